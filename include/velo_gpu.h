@@ -1,0 +1,216 @@
+/*
+ * velo_gpu.h — C ABI of the B200-native VELO front end (libvelo_gpu.so).
+ *
+ * The reference (lichunshang/vision-enhanced-lidar-odometry) has no FFI/plugin
+ * layer: its per-frame front end is a set of free functions textually included
+ * into main.cpp (main.cpp:53-57).  This header is the C-ABI a maintainer binds
+ * instead; include/velo_dropin.hpp keeps the reference's C++ signatures on top
+ * of it.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, POD only, no exceptions; every call returns a velo_status
+ *     (0 = OK) and records a message readable with velo_gpu_last_error().
+ *   - one context per GPU; contexts are independent (one host thread per GPU).
+ *   - calls are asynchronous on the context's stream unless they return data
+ *     into host memory, in which case they synchronise before returning.
+ *   - "slot" = a device-resident scan (the GPU analogue of lru.h's ScanData):
+ *     ring-segmented points + neighbour index + per-camera projections.
+ *   - there is NO CPU fallback: without a CUDA device velo_gpu_create fails.
+ */
+#ifndef VELO_GPU_H
+#define VELO_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VELO_GPU_ABI_VERSION 1
+#define VELO_MAX_CAMS 4          /* kitti.h:4  num_cams_actual */
+#define VELO_NUM_KP_SETS 2       /* main.cpp:261 (after tracking) and main.cpp:600 (after detection) */
+#define VELO_NEQ 28              /* 21 upper-triangular JtJ + 6 Jtr + 1 cost */
+#define VELO_NEQ_STRIDE 64       /* doubles per normal-equation record: [0,28) robustified, [28,56) raw, [56] n_blocks, [57] n_residuals, [58] n_queries */
+
+typedef enum velo_status {
+    VELO_OK = 0,
+    VELO_ERR_NO_DEVICE = 1,      /* no CUDA device / wrong architecture: there is no CPU fallback */
+    VELO_ERR_CUDA = 2,
+    VELO_ERR_INVALID_ARG = 3,
+    VELO_ERR_CAPACITY = 4,       /* more points / rings / features than the context was created for */
+    VELO_ERR_STATE = 5           /* e.g. associate before project */
+} velo_status;
+
+/* residual type tags, same order as velo.h:3-8 (+3DPD) */
+enum { VELO_RES_3D3D = 0, VELO_RES_3D2D = 1, VELO_RES_2D3D = 2, VELO_RES_2D2D = 3, VELO_RES_3DPD = 4 };
+
+/* Tunables: defaults equal kitti.h:3-35 and the feature macros of main.cpp:42-49. */
+typedef struct velo_gpu_params {
+    int num_cams;                 /* kitti.h:3   (2) */
+    int icp_skip;                 /* kitti.h:8   (200); BASELINE configs use 1 */
+    int f2f_iterations;           /* kitti.h:9   (2) */
+    int icp_iterations;           /* kitti.h:10  (3) */
+    int enable_2d2d;              /* main.cpp:44 (1) */
+    int enable_3d2d;              /* main.cpp:45 (1) */
+    int abs_truncates;            /* SURVEY hazard H1: 1 = unqualified abs() bound to int abs(int) (velo.h:416,419,709) */
+    int reserved0;
+    double weight_3D2D;           /* kitti.h:20-35 */
+    double weight_2D2D;
+    double weight_3DPD;
+    double loss_thresh_3D2D;
+    double loss_thresh_2D2D;
+    double loss_thresh_3DPD;
+    double loss_thresh_3D3D;
+    double depth_assoc_thresh;
+    double outlier_reject;
+    double correspondence_thresh_icp;
+    double icp_norm_condition;
+    /* capacities of the context (device memory is allocated once at create) */
+    int max_slots;                /* device-resident scans (lru.h:33 keeps 50) */
+    int max_points;               /* per scan; lru.h:5 says ~130 000 */
+    int max_rings;                /* ring count is data dependent (kitti.h:166-173) */
+    int max_features;             /* per image per set; kitti.h:7 corner_count = 3000 */
+    int max_matches;              /* per camera per frame pair */
+    int max_icp_passes;           /* f2f_iterations * icp_iterations per batched call */
+    int ctas_per_icp_unit;        /* CTAs cooperating on one (frame, pass); 0 = auto */
+    int reserved1;
+} velo_gpu_params;
+
+/* Calibration, the kitti.h:40-51 globals packed for the device. */
+typedef struct velo_gpu_calib {
+    float velo_to_cam[16];            /* row-major 4x4, kitti.h:100-105 */
+    float cam_trans[VELO_MAX_CAMS][4];/* K^-1 * P[:,3], kitti.h:74-78 (w unused) */
+    float cam_K[VELO_MAX_CAMS][9];    /* cam_intrinsic, kitti.h:80 */
+    float cam_Kinv[VELO_MAX_CAMS][9]; /* cam_intrinsic_inv, kitti.h:81 */
+    double min_x[VELO_MAX_CAMS], max_x[VELO_MAX_CAMS];  /* kitti.h:87-97 (stored as double, kitti.h:51) */
+    double min_y[VELO_MAX_CAMS], max_y[VELO_MAX_CAMS];
+    int img_width, img_height;        /* kitti.h:37-38, overwritten by loadImage kitti.h:196-197 */
+} velo_gpu_calib;
+
+/* One ICP correspondence (velo.h:806-874 locals), for parity checks. */
+typedef struct velo_icp_corr {
+    int32_t src_ring, src_idx;        /* sm, smi */
+    int32_t np_s_i, np_i;             /* best ring / point        velo.h:836-842 */
+    int32_t np_s_j, np_j;             /* runner-up ring / point   velo.h:843-847 */
+    int32_t np_k;                     /* third point on ring np_s_i, velo.h:852-863 */
+    int32_t kept;                     /* 0: <2 rings (velo.h:849), 2: degenerate normal (velo.h:873), 1: residual block added */
+    float   normal[3];                /* velo.h:868-874 */
+    float   v0[3];                    /* plane offset, velo.h:865 */
+    double  residual;                 /* cost3DPD at the supplied pose, costfunctions.h:40-53 */
+    double  jacobian[6];              /* d residual / d (angle-axis, translation) */
+} velo_icp_corr;
+
+/* One visual residual block (velo.h:662-789), in residualStats order (velo.h:934-976). */
+typedef struct velo_vis_block {
+    int32_t cam, match;               /* index into the match list of that camera */
+    int32_t type, n_res;              /* VELO_RES_*, 3/2/2/1 */
+    double  residual[3];
+    double  jacobian[18];             /* row-major n_res x 6 */
+} velo_vis_block;
+
+typedef struct velo_gpu_ctx velo_gpu_ctx;
+
+/* ---------------------------------------------------------------- lifecycle */
+int  velo_gpu_abi_version(void);
+/* kitti.h:3-35 defaults + capacities for one KITTI frame pair */
+int  velo_gpu_default_params(velo_gpu_params *p);
+/* replaces loadCalibration (kitti.h:59-108): P = 4 x (3x4 row-major), Tr = 3x4 row-major */
+int  velo_gpu_calib_from_kitti(const float P[48], const float Tr[12], int img_width, int img_height,
+                               velo_gpu_calib *out);
+/* pixel2canonical / canonical2pixel (velo.h:10-26): n points, interleaved (x,y) */
+int  velo_pixel2canonical(const velo_gpu_calib *calib, int cam, const float *pix, int n, float *canon);
+int  velo_canonical2pixel(const velo_gpu_calib *calib, int cam, const float *canon, int n, float *pix);
+
+int  velo_gpu_create(int device, const velo_gpu_params *params, const velo_gpu_calib *calib, velo_gpu_ctx **out);
+int  velo_gpu_destroy(velo_gpu_ctx *ctx);
+const char *velo_gpu_last_error(const velo_gpu_ctx *ctx); /* ctx may be NULL: message of a failed create */
+int  velo_gpu_sync(velo_gpu_ctx *ctx);
+int  velo_gpu_device_name(velo_gpu_ctx *ctx, char *buf, int buflen);
+
+/* pinned host memory for the batched path */
+int  velo_gpu_host_alloc(void **ptr, uint64_t bytes);
+int  velo_gpu_host_free(void *ptr);
+
+/* device timing on the context's stream (CUDA events) */
+int  velo_gpu_timer_begin(velo_gpu_ctx *ctx);
+int  velo_gpu_timer_end(velo_gpu_ctx *ctx, float *ms);   /* synchronises */
+/* per-kernel accumulated device time since the last reset; names via velo_gpu_kernel_name */
+#define VELO_NUM_KERNELS 12
+int  velo_gpu_profile_enable(velo_gpu_ctx *ctx, int on);
+int  velo_gpu_profile_reset(velo_gpu_ctx *ctx);
+int  velo_gpu_profile_read(velo_gpu_ctx *ctx, float ms[VELO_NUM_KERNELS], int launches[VELO_NUM_KERNELS]); /* synchronises */
+const char *velo_gpu_kernel_name(int k);
+
+/* ---------------------------------------------------------------- single-frame path (drop-in) */
+/* ScanData ctor (lru.h:12-28): loadPoints layout (kitti.h:121-152) -> segmentPoints (kitti.h:154-185)
+ * -> neighbour index (replaces 64x KdTreeFLANN::setInputCloud, lru.h:17-20).  xyzr: n x float4. */
+int  velo_gpu_scan_upload(velo_gpu_ctx *ctx, int slot, const float *xyzr, int n);
+int  velo_gpu_scan_info(velo_gpu_ctx *ctx, int slot, int *n_points, int *n_rings);
+/* ring-ordered cam-0-frame points (n x {x,y,z,1}) and ring_start[n_rings+1] — the `scans` vector of kitti.h:156 */
+int  velo_gpu_scan_download(velo_gpu_ctx *ctx, int slot, float *xyz1, int *ring_start);
+
+/* projectLidarToCamera (velo.h:329-375) for camera `cam`; results stay on the device */
+int  velo_gpu_project(velo_gpu_ctx *ctx, int slot, int cam);
+/* ring_count[n_rings]; proj: total x (x,y); valid: total x {x,y,z,1}, rings concatenated in order */
+int  velo_gpu_project_download(velo_gpu_ctx *ctx, int slot, int cam, int *ring_count, float *proj, float *valid, int *total);
+
+/* featureDepthAssociation (velo.h:377-497): kp = F x (x,y) canonical; has_depth[F]; kpwd = n_hits x {x,y,z,1} */
+int  velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int set, const float *kp, int F,
+                          int *has_depth, float *kpwd, int *n_hits);
+
+/* ICP block of frameToFrame (velo.h:800-895) at a supplied pose: transform_point (utility.h:97-103),
+ * per-ring 1-NN + top-2 rings + third point + normal (velo.h:806-874), cost3DPD residual/Jacobian
+ * (costfunctions.h:17-58) and the normal equations Ceres would form (velo.h:885-902).
+ * slot_M = current frame (queries), slot_S = previous frame (targets + index).
+ * corr may be NULL; otherwise capacity must be >= number of queries (sum over rings of ceil(len/icp_skip)).
+ * neq: VELO_NEQ_STRIDE doubles. */
+int  velo_gpu_icp_pass(velo_gpu_ctx *ctx, int slot_M, int slot_S, const double pose[6], int iter, int icp_skip,
+                       velo_icp_corr *corr, int corr_capacity, int *n_queries, int *n_kept, double *neq);
+
+/* visual residual assembly of frameToFrame (velo.h:622-792) for all cameras at a supplied pose.
+ * Frame1 = (slot1,set1) current, frame2 = (slot2,set2) previous: their keypoints / has_depth / kp_with_depth
+ * are the device-resident results of velo_gpu_depth_assoc.  matches: per camera n_matches[c] pairs
+ * (point1, point2) stored consecutively; lm_valid/lm_xyz (nullable) = landmarks_at_frame lookup per match
+ * (velo.h:634-644), lm_xyz = {x,y,z,1} per match.
+ * blocks (nullable, capacity 3 per match) receive the residual blocks in residualStats order. */
+int  velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1, int slot2, int set2,
+                               const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
+                               const double pose[6], int iter,
+                               velo_vis_block *blocks, int block_capacity, int *n_blocks, double *neq);
+
+/* ---------------------------------------------------------------- batched path (throughput) */
+/* A batch is `count` consecutive slots starting at slot0.  Inputs are concatenated with fixed strides:
+ *   scans   [count][max_points][4] float,   n_points[count]
+ *   kp      [count][VELO_NUM_KP_SETS][num_cams][max_features][2] float, n_kp[count][sets][cams]
+ *   matches [count][num_cams][max_matches][2] int, n_matches[count][cams]   (frame pair slot s / slot s-1)
+ *   poses   [count][n_passes][6] double, pass_iter[n_passes]  (iter value of each ICP pass)
+ *   vis_poses [count][f2f_iterations][6] double
+ * Pointers are HOST pointers (pinned preferred); upload copies them to device staging. */
+typedef struct velo_batch_inputs {
+    const float  *scans;     const int *n_points;
+    const float  *kp;        const int *n_kp;
+    const int    *matches;   const int *n_matches;
+    const double *icp_poses; const int *pass_iter; int n_passes;
+    const double *vis_poses; int n_vis_iters;
+} velo_batch_inputs;
+
+int  velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in);
+/* stages bitmask */
+enum { VELO_STAGE_INGEST = 1, VELO_STAGE_INDEX = 2, VELO_STAGE_PROJECT = 4, VELO_STAGE_ASSOC = 8,
+       VELO_STAGE_ICP = 16, VELO_STAGE_VISUAL = 32, VELO_STAGE_ALL = 63 };
+/* runs the selected stages for slots [slot0, slot0+count).  ICP/visual pair slot s with slot s-1 and are
+ * skipped for the first slot of the batch when first_has_prev == 0. */
+int  velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int first_has_prev);
+/* icp_neq [count][n_passes][VELO_NEQ_STRIDE], vis_neq [count][n_vis_iters][VELO_NEQ_STRIDE],
+ * has_depth [count][sets][cams][max_features], n_hits [count][sets][cams]; any pointer may be NULL. Synchronises. */
+int  velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *icp_neq, double *vis_neq,
+                             int *has_depth, int *n_hits);
+/* number of kernel launches issued by this context since creation */
+int  velo_gpu_launch_count(velo_gpu_ctx *ctx, int64_t *launches);
+/* algorithmic bytes moved by kernel class k since the last profile reset */
+int  velo_gpu_profile_bytes(velo_gpu_ctx *ctx, double bytes[VELO_NUM_KERNELS]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELO_GPU_H */

@@ -207,8 +207,9 @@ int  velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *ic
                              int *has_depth, int *n_hits);
 /* number of kernel launches issued by this context since creation */
 int  velo_gpu_launch_count(velo_gpu_ctx *ctx, int64_t *launches);
-/* algorithmic bytes moved by kernel class k since the last profile reset */
-int  velo_gpu_profile_bytes(velo_gpu_ctx *ctx, double bytes[VELO_NUM_KERNELS]);
+/* per-slot counts needed to state algorithmic bytes: n_points[count], n_rings[count],
+ * proj_total[count][num_cams] (in-FOV survivors M), status[count] (velo_status per scan). Synchronises. */
+int  velo_gpu_batch_counts(velo_gpu_ctx *ctx, int slot0, int count, int *n_points, int *n_rings, int *proj_total, int *status);
 
 #ifdef __cplusplus
 }

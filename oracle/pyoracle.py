@@ -1,0 +1,266 @@
+"""ctypes wrappers for the CPU oracle (libvelo_oracle.so) and, when built, the reference-slice library
+(oracle/_ref/libvelo_ref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import importlib
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+abi = importlib.import_module("vision-enhanced-lidar-odometry_b200.abi")
+
+ORACLE_LIB = os.path.join(HERE, "libvelo_oracle.so")
+REF_LIB = os.path.join(HERE, "_ref", "libvelo_ref.so")
+
+
+def build_oracle(force=False):
+    src = os.path.join(HERE, "velo_oracle.cpp")
+    hdr = os.path.join(ROOT, "include", "velo_gpu.h")
+    fresh = os.path.isfile(ORACLE_LIB) and all(os.path.getmtime(ORACLE_LIB) >= os.path.getmtime(s) for s in (src, hdr))
+    if fresh and not force:
+        return ORACLE_LIB
+    if shutil.which("g++") is None and os.path.isfile(ORACLE_LIB):
+        return ORACLE_LIB
+    # no -march, no FMA contraction: mirrors the reference build (CMakeLists.txt:30)
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w",
+                    "-o", ORACLE_LIB, src], check=True)
+    return ORACLE_LIB
+
+
+def build_ref(force=False):
+    sys.path.insert(0, HERE)
+    import build_ref as br
+    return br.build(force)
+
+
+_P = C.c_void_p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.oracle_segment.argtypes = [_P, C.c_int, _P, _P, _P, C.c_int]
+        L.oracle_project.argtypes = [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P]
+        L.oracle_depth_assoc.argtypes = [_P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _P, _P]
+        L.oracle_transform_points.argtypes = [_P, C.c_int, _P, _P]
+        L.oracle_icp_pass.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]
+        L.oracle_nn_selfcheck.argtypes = [_P, C.c_int, _P, C.c_int]
+        L.oracle_eval_functor.argtypes = [C.c_int, _P, _P, _P, _P]
+        L.oracle_loss.argtypes = [C.c_int, C.c_double, C.c_double, _P]
+        L.oracle_visual.argtypes = [C.c_int, C.c_int, C.c_int] + [_P] * 10 + [_P, _P, _P, C.c_int, _P, C.c_int, _P]
+        L.oracle_calib_from_kitti.argtypes = [_P, _P, C.c_int, C.c_int, _P]
+        L.oracle_pixel2canonical.argtypes = [_P, C.c_int, _P, C.c_int, _P]
+        L.oracle_canonical2pixel.argtypes = [_P, C.c_int, _P, C.c_int, _P]
+        L.oracle_bench_frames.restype = C.c_double
+        L.oracle_bench_frames.argtypes = [C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]
+
+    # ---- a1
+    def calib_from_kitti(self, P, Tr, w, h):
+        cal = abi.Calib()
+        self.lib.oracle_calib_from_kitti(_ptr(np.ascontiguousarray(P, np.float32)), _ptr(np.ascontiguousarray(Tr, np.float32)), w, h, C.addressof(cal))
+        return cal
+
+    def pixel2canonical(self, cal, cam, pix):
+        pix = np.ascontiguousarray(pix, np.float32)
+        out = np.zeros_like(pix)
+        self.lib.oracle_pixel2canonical(C.addressof(cal), cam, _ptr(pix), len(pix), _ptr(out))
+        return out
+
+    def canonical2pixel(self, cal, cam, can):
+        can = np.ascontiguousarray(can, np.float32)
+        out = np.zeros_like(can)
+        self.lib.oracle_canonical2pixel(C.addressof(cal), cam, _ptr(can), len(can), _ptr(out))
+        return out
+
+    # ---- a3
+    def segment(self, xyzr, cal, max_rings=4096):
+        xyzr = np.ascontiguousarray(xyzr, np.float32)
+        n = len(xyzr)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        rs = np.zeros(max_rings + 1, np.int32)
+        nr = self.lib.oracle_segment(_ptr(xyzr), n, C.addressof(cal), _ptr(out), _ptr(rs), max_rings)
+        return out[:n], rs[:min(nr, max_rings) + 1].copy(), nr
+
+    # ---- a5
+    def project(self, pts, rs, cal, cam):
+        pts = np.ascontiguousarray(pts, np.float32)
+        rs = np.ascontiguousarray(rs, np.int32)
+        nr, n = len(rs) - 1, len(pts)
+        rc = np.zeros(max(nr, 1), np.int32)
+        proj = np.zeros((max(n, 1), 2), np.float32)
+        valid = np.zeros((max(n, 1), 4), np.float32)
+        tot = self.lib.oracle_project(_ptr(pts), _ptr(rs), nr, C.addressof(cal), cam, _ptr(rc), _ptr(proj), _ptr(valid))
+        return rc[:nr], proj[:tot], valid[:tot]
+
+    # ---- a7
+    def depth_assoc(self, valid, proj, rc, kp, thresh=0.015, abs_truncates=0):
+        valid = np.ascontiguousarray(valid, np.float32)
+        proj = np.ascontiguousarray(proj, np.float32)
+        rc = np.ascontiguousarray(rc, np.int32)
+        kp = np.ascontiguousarray(kp, np.float32)
+        F = len(kp)
+        hd = np.zeros(max(F, 1), np.int32)
+        kpwd = np.zeros((max(F, 1), 4), np.float32)
+        nh = self.lib.oracle_depth_assoc(_ptr(valid), _ptr(proj), _ptr(rc), len(rc), _ptr(kp), F, thresh, abs_truncates, _ptr(hd), _ptr(kpwd))
+        return hd[:F], kpwd[:nh]
+
+    def transform_points(self, pts, pose):
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.zeros_like(pts)
+        pose = np.ascontiguousarray(pose, np.float64)
+        self.lib.oracle_transform_points(_ptr(pts), len(pts), _ptr(pose), _ptr(out))
+        return out
+
+    # ---- a10/a11/a13
+    def icp_pass(self, ptsM, rsM, ptsS, rsS, pose, it, skip, prm, mode=1):
+        ptsM = np.ascontiguousarray(ptsM, np.float32); rsM = np.ascontiguousarray(rsM, np.int32)
+        ptsS = np.ascontiguousarray(ptsS, np.float32); rsS = np.ascontiguousarray(rsS, np.int32)
+        pose = np.ascontiguousarray(pose, np.float64)
+        nq = int(sum(-(-int(l) // skip) for l in np.diff(rsM)))
+        corr = np.zeros(max(nq, 1), abi.ICP_CORR_DTYPE)
+        neq = np.zeros(abi.NEQ_STRIDE, np.float64)
+        kept = C.c_int()
+        q = self.lib.oracle_icp_pass(_ptr(ptsM), _ptr(rsM), len(rsM) - 1, _ptr(ptsS), _ptr(rsS), len(rsS) - 1, _ptr(pose), it, skip,
+                                     C.addressof(prm), mode, _ptr(corr), C.addressof(kept), _ptr(neq))
+        assert q == nq, (q, nq)
+        return corr[:nq], neq, kept.value
+
+    def nn_selfcheck(self, pts, queries):
+        pts = np.ascontiguousarray(pts, np.float32); queries = np.ascontiguousarray(queries, np.float32)
+        return self.lib.oracle_nn_selfcheck(_ptr(pts), len(pts), _ptr(queries), len(queries))
+
+    def eval_functor(self, typ, k, pose):
+        k = np.ascontiguousarray(k, np.float64); pose = np.ascontiguousarray(pose, np.float64)
+        r = np.zeros(3); J = np.zeros(18)
+        nr = self.lib.oracle_eval_functor(typ, _ptr(k), _ptr(pose), _ptr(r), _ptr(J))
+        return r[:nr].copy(), J[:6 * nr].reshape(nr, 6).copy()
+
+    def loss(self, kind, a, s):
+        rho = np.zeros(3)
+        self.lib.oracle_loss(kind, a, s, _ptr(rho))
+        return rho
+
+    # ---- a12/a13
+    def visual(self, kp1, kp2, hd1, hd2, kpwd1, kpwd2, n_matches, matches, cal, prm, pose, it, lm_valid=None, lm_xyz=None, _lib=None, _fn="oracle_visual"):
+        """kp*: [C][F][2], hd*: [C][F], kpwd*: [C][F][4], matches: [C][MM][2], n_matches[C]"""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        kp1, kp2, kpwd1, kpwd2 = f32(kp1), f32(kp2), f32(kpwd1), f32(kpwd2)
+        hd1, hd2, matches, n_matches = i32(hd1), i32(hd2), i32(matches), i32(n_matches)
+        ncam, F = kp1.shape[0], kp1.shape[1]
+        MM = matches.shape[1]
+        lm_valid = None if lm_valid is None else i32(lm_valid)
+        lm_xyz = None if lm_xyz is None else f32(lm_xyz)
+        cap = 3 * int(n_matches.sum()) + 1
+        blocks = np.zeros(cap, abi.VIS_BLOCK_DTYPE)
+        neq = np.zeros(abi.NEQ_STRIDE, np.float64)
+        pose = np.ascontiguousarray(pose, np.float64)
+        if _fn == "oracle_visual":
+            nb = self.lib.oracle_visual(ncam, F, MM, _ptr(kp1), _ptr(kp2), _ptr(hd1), _ptr(hd2), _ptr(kpwd1), _ptr(kpwd2), _ptr(n_matches), _ptr(matches),
+                                        _ptr(lm_valid), _ptr(lm_xyz), C.addressof(cal), C.addressof(prm), _ptr(pose), it, _ptr(blocks), cap, _ptr(neq))
+        else:
+            nb = _lib.ref_visual(ncam, F, MM, _ptr(kp1), _ptr(kp2), _ptr(hd1), _ptr(hd2), _ptr(kpwd1), _ptr(kpwd2), _ptr(n_matches), _ptr(matches),
+                                 _ptr(lm_valid), _ptr(lm_xyz), C.addressof(cal), _ptr(pose), it, _ptr(blocks), cap, _ptr(neq))
+        return blocks[:nb], neq
+
+    # ---- timed CPU baseline
+    def bench_frames(self, batch, prm, cal, threads, stages=abi.STAGE_ALL, want_out=False):
+        bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
+                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis)
+        icp = np.zeros((batch.count, batch.n_passes, abi.NEQ_STRIDE)) if want_out else None
+        vis = np.zeros((batch.count, batch.n_vis, abi.NEQ_STRIDE)) if want_out else None
+        sec = self.lib.oracle_bench_frames(batch.count, threads, C.addressof(prm), C.addressof(cal), C.addressof(bi), stages, _ptr(icp), _ptr(vis))
+        return sec, icp, vis
+
+
+class Ref:
+    """The reference's own source lines (oracle/_ref/libvelo_ref.so); None-like when not built."""
+
+    def __init__(self):
+        if not os.path.isfile(REF_LIB):
+            build_ref()
+        if not os.path.isfile(REF_LIB):
+            raise FileNotFoundError(REF_LIB)
+        self.lib = C.CDLL(REF_LIB)
+        L = self.lib
+        L.ref_segment.argtypes = [_P, C.c_int, _P, _P, _P, C.c_int]
+        L.ref_project.argtypes = [_P, _P, C.c_int, _P, C.c_int, _P, _P, _P]
+        L.ref_depth_assoc.argtypes = [_P, _P, _P, C.c_int, _P, C.c_int, _P, _P]
+        L.ref_transform_points.argtypes = [_P, C.c_int, _P, _P]
+        L.ref_eval_functor.argtypes = [C.c_int, _P, _P, _P, _P]
+        L.ref_eval_functor_plain.argtypes = [C.c_int, _P, _P, _P]
+        L.ref_icp_pass.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, _P]
+        L.ref_visual.argtypes = [C.c_int, C.c_int, C.c_int] + [_P] * 10 + [_P, _P, C.c_int, _P, C.c_int, _P]
+        L.ref_constants.argtypes = [_P]
+
+    def segment(self, xyzr, cal, max_rings=4096):
+        xyzr = np.ascontiguousarray(xyzr, np.float32)
+        n = len(xyzr)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        rs = np.zeros(max_rings + 1, np.int32)
+        nr = self.lib.ref_segment(_ptr(xyzr), n, C.addressof(cal), _ptr(out), _ptr(rs), max_rings)
+        return out[:n], rs[:min(nr, max_rings) + 1].copy(), nr
+
+    def project(self, pts, rs, cal, cam):
+        pts = np.ascontiguousarray(pts, np.float32); rs = np.ascontiguousarray(rs, np.int32)
+        nr, n = len(rs) - 1, len(pts)
+        rc = np.zeros(max(nr, 1), np.int32); proj = np.zeros((max(n, 1), 2), np.float32); valid = np.zeros((max(n, 1), 4), np.float32)
+        tot = self.lib.ref_project(_ptr(pts), _ptr(rs), nr, C.addressof(cal), cam, _ptr(rc), _ptr(proj), _ptr(valid))
+        return rc[:nr], proj[:tot], valid[:tot]
+
+    def depth_assoc(self, valid, proj, rc, kp):
+        valid = np.ascontiguousarray(valid, np.float32); proj = np.ascontiguousarray(proj, np.float32)
+        rc = np.ascontiguousarray(rc, np.int32); kp = np.ascontiguousarray(kp, np.float32)
+        F = len(kp)
+        hd = np.zeros(max(F, 1), np.int32); kpwd = np.zeros((max(F, 1), 4), np.float32)
+        nh = self.lib.ref_depth_assoc(_ptr(valid), _ptr(proj), _ptr(rc), len(rc), _ptr(kp), F, _ptr(hd), _ptr(kpwd))
+        return hd[:F], kpwd[:nh]
+
+    def transform_points(self, pts, pose):
+        pts = np.ascontiguousarray(pts, np.float32); out = np.zeros_like(pts); pose = np.ascontiguousarray(pose, np.float64)
+        self.lib.ref_transform_points(_ptr(pts), len(pts), _ptr(pose), _ptr(out))
+        return out
+
+    def eval_functor(self, typ, k, pose):
+        k = np.ascontiguousarray(k, np.float64); pose = np.ascontiguousarray(pose, np.float64)
+        r = np.zeros(3); J = np.zeros(18)
+        nr = self.lib.ref_eval_functor(typ, _ptr(k), _ptr(pose), _ptr(r), _ptr(J))
+        return r[:nr].copy(), J[:6 * nr].reshape(nr, 6).copy()
+
+    def eval_functor_plain(self, typ, k, pose):
+        k = np.ascontiguousarray(k, np.float64); pose = np.ascontiguousarray(pose, np.float64)
+        r = np.zeros(3)
+        nr = self.lib.ref_eval_functor_plain(typ, _ptr(k), _ptr(pose), _ptr(r))
+        return r[:nr].copy()
+
+    def icp_pass(self, ptsM, rsM, ptsS, rsS, pose, it, skip):
+        ptsM = np.ascontiguousarray(ptsM, np.float32); rsM = np.ascontiguousarray(rsM, np.int32)
+        ptsS = np.ascontiguousarray(ptsS, np.float32); rsS = np.ascontiguousarray(rsS, np.int32)
+        pose = np.ascontiguousarray(pose, np.float64)
+        nq = int(sum(-(-int(l) // skip) for l in np.diff(rsM)))
+        corr = np.zeros(max(nq, 1), abi.ICP_CORR_DTYPE); neq = np.zeros(abi.NEQ_STRIDE, np.float64)
+        k = self.lib.ref_icp_pass(_ptr(ptsM), _ptr(rsM), len(rsM) - 1, _ptr(ptsS), _ptr(rsS), len(rsS) - 1, _ptr(pose), it, skip, _ptr(corr), nq, _ptr(neq))
+        return corr[:k], neq
+
+    def visual(self, oracle, *a, **kw):
+        return Oracle.visual(oracle, *a, _lib=self.lib, _fn="ref_visual", **kw)
+
+    def constants(self):
+        out = np.zeros(32)
+        n = self.lib.ref_constants(_ptr(out))
+        return out[:n]

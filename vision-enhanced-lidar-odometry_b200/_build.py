@@ -1,0 +1,71 @@
+"""In-tree builds: nvcc (sm_100a) for csrc/*.cu -> libvelo_gpu.so, gcc for host/velo_synth.c -> libvelo_synth.so.
+
+Both are plain shared libraries with a C ABI (include/velo_gpu.h); no torch headers are involved.
+"""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+HOST = os.path.join(PKG, "host")
+GPU_LIB = os.path.join(PKG, "libvelo_gpu.so")
+SYNTH_LIB = os.path.join(HOST, "libvelo_synth.so")
+
+# -fmad=false: the reference is an FMA-free x86-64 build (CMakeLists.txt:30); every index-determining
+# float expression must round like it (SURVEY.md hazard H2).
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static",
+]
+
+
+def _newer(out, srcs):
+    return os.path.isfile(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs)
+
+
+def find_nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.isfile(c):
+            return c
+    return None
+
+
+def gpu_sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def gpu_deps():
+    return gpu_sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+        os.path.join(ROOT, "include", "velo_gpu.h")]
+
+
+def build_gpu(force=False, verbose=False):
+    if not force and _newer(GPU_LIB, gpu_deps()):
+        return GPU_LIB
+    nvcc = find_nvcc()
+    if nvcc is None:
+        if os.path.isfile(GPU_LIB):
+            return GPU_LIB  # prebuilt library shipped with the snapshot
+        raise RuntimeError("nvcc not found and libvelo_gpu.so is not built")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-I", os.path.join(ROOT, "include"), "-I", CSRC] + gpu_sources() + ["-o", GPU_LIB]
+    subprocess.run(cmd, check=True)
+    return GPU_LIB
+
+
+def build_synth(force=False):
+    src = os.path.join(HOST, "velo_synth.c")
+    if not force and _newer(SYNTH_LIB, [src]):
+        return SYNTH_LIB
+    if shutil.which("gcc") is None and os.path.isfile(SYNTH_LIB):
+        return SYNTH_LIB
+    subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-o", SYNTH_LIB, src, "-lm"], check=True)
+    return SYNTH_LIB
+
+
+def build_all(force=False, verbose=False):
+    build_synth(force)
+    build_gpu(force, verbose)

@@ -1,0 +1,655 @@
+// velo_api.cu — host side of libvelo_gpu.so: context, device memory, C-ABI entry points (include/velo_gpu.h).
+// No CPU compute path exists here: every stage is a kernel launch; without a CUDA device create() fails.
+#include "velo_dev.cuh"
+#include <math.h>
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_create_error;
+
+struct ProfRec { int k; cudaEvent_t a, b; };
+
+struct velo_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    velo_gpu_params prm;
+    velo_gpu_calib cal;
+    DevCalib dcal;
+    DevBuffers B;
+    std::string err;
+    // ICP / visual unit staging
+    IcpUnit *h_icp_units = nullptr, *d_icp_units = nullptr;
+    VisUnit *h_vis_units = nullptr, *d_vis_units = nullptr;
+    double *d_icp_partial = nullptr, *d_icp_out = nullptr, *d_vis_partial = nullptr, *d_vis_out = nullptr;
+    int icp_partial_ctas = 0, vis_ctas = 0;
+    int batch_passes = 0, batch_vis = 0;
+    velo_icp_corr *d_corr = nullptr;
+    VisMatchOut *d_mout = nullptr;
+    int *d_lm_valid = nullptr; float4 *d_lm_xyz = nullptr;
+    std::vector<int> h_npoints;     // host copy of n_points per slot (single-frame path)
+    // timing
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<ProfRec> recs;
+    cudaEvent_t cur_a = nullptr;
+    int64_t launches = 0;
+    std::vector<void *> allocs;
+};
+
+static int fail(velo_gpu_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, VELO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------------------------------------ float thresholds (hazard H3)
+// smallest float f with (double)f >= d:   for float v,  (double)v <  d  <=>  v <  f   and   (double)v >= d  <=>  v >= f
+static float ceil_to_float(double d) { float f = (float)d; if ((double)f < d) f = nextafterf(f, INFINITY); return f; }
+// largest float f with (double)f <= d:    for float v,  (double)v >  d  <=>  v >  f
+static float floor_to_float(double d) { float f = (float)d; if ((double)f > d) f = nextafterf(f, -INFINITY); return f; }
+
+// ------------------------------------------------------------------------------------------------ a1: calibration (kitti.h:59-108)
+// Eigen::Matrix3f::inverse() (cofactor form) and 3-term fixed-size reductions e0 + (e1 + e2) [Eigen, SURVEY.md §8 a1]
+static inline float s3(float a, float b, float c) { return a + (b + c); }
+static inline float cofac(const float *m, int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[3 * i1 + j1] * m[3 * i2 + j2] - m[3 * i1 + j2] * m[3 * i2 + j1];
+}
+static void inverse3(const float *m, float *r) {
+    const float c0 = cofac(m, 0, 0), c1 = cofac(m, 1, 0), c2 = cofac(m, 2, 0);
+    const float det = s3(c0 * m[0], c1 * m[3], c2 * m[6]), id = 1.0f / det;
+    r[0] = c0 * id; r[1] = c1 * id; r[2] = c2 * id;
+    for (int row = 1; row < 3; row++) for (int col = 0; col < 3; col++) r[3 * row + col] = cofac(m, col, row) * id;
+}
+static void matvec3(const float *m, const float *v, float *o) {
+    for (int i = 0; i < 3; i++) o[i] = s3(m[3 * i] * v[0], m[3 * i + 1] * v[1], m[3 * i + 2] * v[2]);
+}
+
+extern "C" int velo_gpu_abi_version(void) { return VELO_GPU_ABI_VERSION; }
+
+extern "C" int velo_gpu_default_params(velo_gpu_params *p) {
+    if (!p) return VELO_ERR_INVALID_ARG;
+    memset(p, 0, sizeof(*p));
+    p->num_cams = 2; p->icp_skip = 200; p->f2f_iterations = 2; p->icp_iterations = 3;     // kitti.h:3,8-10
+    p->enable_2d2d = 1; p->enable_3d2d = 1; p->abs_truncates = 0;                          // main.cpp:44-45
+    p->weight_3D2D = 10; p->weight_2D2D = 500; p->weight_3DPD = 1;                         // kitti.h:20-22
+    p->loss_thresh_3D2D = 0.01; p->loss_thresh_2D2D = 0.00002; p->loss_thresh_3DPD = 0.1; p->loss_thresh_3D3D = 0.04; // kitti.h:23-26
+    p->depth_assoc_thresh = 0.015; p->outlier_reject = 5.0; p->correspondence_thresh_icp = 0.5; p->icp_norm_condition = 1e-5; // kitti.h:28-32
+    p->max_slots = 4; p->max_points = 131072; p->max_rings = 128; p->max_features = 3000;  // kitti.h:7
+    p->max_matches = 3000; p->max_icp_passes = 6; p->ctas_per_icp_unit = 0;
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_calib_from_kitti(const float P[48], const float Tr[12], int w, int h, velo_gpu_calib *c) {
+    if (!P || !Tr || !c) return VELO_ERR_INVALID_ARG;
+    memset(c, 0, sizeof(*c));
+    for (int cam = 0; cam < VELO_MAX_CAMS; cam++) {
+        const float *p = P + 12 * cam;
+        const float K[9] = { p[0], p[1], p[2], p[4], p[5], p[6], p[8], p[9], p[10] };
+        const float Kt[3] = { p[3], p[7], p[11] };
+        float Ki[9], t[3];
+        inverse3(K, Ki);
+        matvec3(Ki, Kt, t);                                       // cam_trans = K^-1 * P[:,3]
+        memcpy(c->cam_K[cam], K, sizeof(K)); memcpy(c->cam_Kinv[cam], Ki, sizeof(Ki));
+        for (int i = 0; i < 3; i++) c->cam_trans[cam][i] = t[i];
+        const float lo[3] = { 0.f, 0.f, 1.f }, hi[3] = { (float)w, (float)h, 1.f };
+        float a[3], b[3];
+        matvec3(Ki, lo, a); matvec3(Ki, hi, b);
+        c->min_x[cam] = a[0] / a[2]; c->min_y[cam] = a[1] / a[2];
+        c->max_x[cam] = b[0] / b[2]; c->max_y[cam] = b[1] / b[2];
+    }
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) c->velo_to_cam[4 * i + j] = (i < 3) ? Tr[4 * i + j] : (j == 3 ? 1.f : 0.f);
+    c->img_width = w; c->img_height = h;
+    return VELO_OK;
+}
+
+extern "C" int velo_pixel2canonical(const velo_gpu_calib *c, int cam, const float *pix, int n, float *out) {  // velo.h:10-17
+    if (!c || cam < 0 || cam >= VELO_MAX_CAMS || (n > 0 && (!pix || !out))) return VELO_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++) { const float v[3] = { pix[2 * i], pix[2 * i + 1], 1.f }; float p[3]; matvec3(c->cam_Kinv[cam], v, p); out[2 * i] = p[0] / p[2]; out[2 * i + 1] = p[1] / p[2]; }
+    return VELO_OK;
+}
+extern "C" int velo_canonical2pixel(const velo_gpu_calib *c, int cam, const float *can, int n, float *out) {  // velo.h:19-26
+    if (!c || cam < 0 || cam >= VELO_MAX_CAMS || (n > 0 && (!can || !out))) return VELO_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++) { const float v[3] = { can[2 * i], can[2 * i + 1], 1.f }; float p[3]; matvec3(c->cam_K[cam], v, p); out[2 * i] = p[0] / p[2]; out[2 * i + 1] = p[1] / p[2]; }
+    return VELO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pose constants (hazard H8)
+namespace {
+struct J3 { double a, v[3]; };
+inline J3 j3(double s) { return J3{ s, { 0, 0, 0 } }; }
+inline J3 operator+(J3 x, J3 y) { return J3{ x.a + y.a, { x.v[0] + y.v[0], x.v[1] + y.v[1], x.v[2] + y.v[2] } }; }
+inline J3 operator-(J3 x, J3 y) { return J3{ x.a - y.a, { x.v[0] - y.v[0], x.v[1] - y.v[1], x.v[2] - y.v[2] } }; }
+inline J3 operator*(J3 x, J3 y) { return J3{ x.a * y.a, { x.a * y.v[0] + x.v[0] * y.a, x.a * y.v[1] + x.v[1] * y.a, x.a * y.v[2] + x.v[2] * y.a } }; }
+inline J3 operator/(J3 x, J3 y) { const double inv = 1.0 / y.a, q = x.a * inv; return J3{ q, { (x.v[0] - q * y.v[0]) * inv, (x.v[1] - q * y.v[1]) * inv, (x.v[2] - q * y.v[2]) * inv } }; }
+inline J3 jsqrt(J3 x) { const double r = sqrt(x.a), d = 1.0 / (2.0 * r); return J3{ r, { x.v[0] * d, x.v[1] * d, x.v[2] * d } }; }
+inline J3 jsin(J3 x) { const double c = cos(x.a); return J3{ sin(x.a), { c * x.v[0], c * x.v[1], c * x.v[2] } }; }
+inline J3 jcos(J3 x) { const double s = -sin(x.a); return J3{ cos(x.a), { s * x.v[0], s * x.v[1], s * x.v[2] } }; }
+
+// AngleAxisRotatePoint on 3-partial dual numbers: derivative of R(w) e_j w.r.t. w
+void rotate_j3(const J3 w[3], const J3 p[3], J3 out[3]) {
+    const J3 th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    if (th2.a > DBL_EPSILON) {
+        const J3 th = jsqrt(th2), c = jcos(th), s = jsin(th), ith = j3(1.0) / th;
+        const J3 u[3] = { w[0] * ith, w[1] * ith, w[2] * ith };
+        const J3 x[3] = { u[1] * p[2] - u[2] * p[1], u[2] * p[0] - u[0] * p[2], u[0] * p[1] - u[1] * p[0] };
+        const J3 tmp = (u[0] * p[0] + u[1] * p[1] + u[2] * p[2]) * (j3(1.0) - c);
+        for (int i = 0; i < 3; i++) out[i] = p[i] * c + x[i] * s + u[i] * tmp;
+    } else {
+        out[0] = p[0] + (w[1] * p[2] - w[2] * p[1]);
+        out[1] = p[1] + (w[2] * p[0] - w[0] * p[2]);
+        out[2] = p[2] + (w[0] * p[1] - w[1] * p[0]);
+    }
+}
+
+void make_pose_pack(const double pose[6], PosePack *P) {
+    memset(P, 0, sizeof(*P));
+    for (int i = 0; i < 3; i++) { P->w[i] = pose[i]; P->t[i] = pose[3 + i]; }
+    const double th2 = pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2];
+    P->small_angle = !(th2 > DBL_EPSILON);
+    if (!P->small_angle) {
+        const double th = sqrt(th2);
+        P->c = cos(th); P->s = sin(th);
+        const double ith = 1.0 / th;
+        for (int i = 0; i < 3; i++) P->u[i] = pose[i] * ith;
+    } else { P->c = 1.0; P->s = 0.0; }
+    J3 w[3];
+    for (int k = 0; k < 3; k++) { w[k] = j3(pose[k]); w[k].v[k] = 1.0; }
+    for (int j = 0; j < 3; j++) {
+        J3 e[3] = { j3(j == 0), j3(j == 1), j3(j == 2) }, o[3];
+        rotate_j3(w, e, o);
+        for (int k = 0; k < 3; k++) for (int i = 0; i < 3; i++) P->dR[9 * k + 3 * i + j] = o[i].v[k];
+    }
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ profiling hooks
+static const char *k_names[VELO_NUM_KERNELS] = { "ingest_flags", "ingest_rings", "ingest_permute", "index_build", "project_occlude",
+                                                 "assoc_search", "assoc_compact", "icp_pass", "neq_reduce", "visual_residuals", "misc0", "misc1" };
+extern "C" const char *velo_gpu_kernel_name(int k) { return (k >= 0 && k < VELO_NUM_KERNELS) ? k_names[k] : ""; }
+
+static cudaEvent_t get_event(velo_gpu_ctx *c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+static void prof_pre(void *u, int k) {
+    velo_gpu_ctx *c = (velo_gpu_ctx *)u; c->launches++;
+    if (!c->profile) return;
+    c->cur_a = get_event(c); cudaEventRecord(c->cur_a, c->stream);
+}
+static void prof_post(void *u, int k) {
+    velo_gpu_ctx *c = (velo_gpu_ctx *)u;
+    if (!c->profile) return;
+    cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream);
+    c->recs.push_back(ProfRec{ k, c->cur_a, b });
+}
+static Launcher launcher(velo_gpu_ctx *c) { return Launcher{ c->stream, prof_pre, prof_post, c }; }
+
+// ------------------------------------------------------------------------------------------------ lifecycle
+template <class T> static cudaError_t dalloc(velo_gpu_ctx *c, T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) { c->allocs.push_back(*p); e = cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream); }
+    return e;
+}
+
+extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const velo_gpu_calib *cal, velo_gpu_ctx **out) {
+    velo_gpu_ctx *ctx = nullptr;
+    if (!prm || !cal || !out) return fail(nullptr, VELO_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (prm->num_cams < 1 || prm->num_cams > VELO_MAX_CAMS || prm->max_rings < 1 || prm->max_rings > VELO_MAX_RINGS_HARD ||
+        prm->max_points < 1 || prm->max_points > (1 << VELO_IDX_BITS) || prm->max_slots < 1 || prm->max_features < 1 ||
+        prm->max_matches < 1 || prm->max_icp_passes < 1 || prm->icp_skip < 1)
+        return fail(nullptr, VELO_ERR_INVALID_ARG, "parameter out of range (num_cams 1..4, max_rings 1..256, max_points 1..2^20, ...)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VELO_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "); libvelo_gpu has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, VELO_ERR_INVALID_ARG, "device index out of range");
+    cudaDeviceProp dp;
+    if (cudaGetDeviceProperties(&dp, device) != cudaSuccess || dp.major != 10)
+        return fail(nullptr, VELO_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+    ctx = new velo_gpu_ctx();
+    ctx->device = device; ctx->prm = *prm; ctx->cal = *cal;
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); velo_gpu_destroy(ctx); return fail(nullptr, VELO_ERR_CUDA, m); } } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&ctx->t0)); CKC(cudaEventCreate(&ctx->t1));
+    DevBuffers &B = ctx->B;
+    memset(&B, 0, sizeof(B));
+    B.S = prm->max_slots; B.N = (prm->max_points + 127) & ~127; B.R = prm->max_rings; B.C = prm->num_cams;
+    B.F = prm->max_features; B.MM = prm->max_matches; B.P = prm->max_icp_passes;
+    const size_t S = B.S, N = B.N, R = B.R, C = B.C, F = B.F, MM = B.MM, P = B.P;
+    CKC(dalloc(ctx, &B.raw, S * N)); CKC(dalloc(ctx, &B.flagbits, S * (N / 32)));
+    CKC(dalloc(ctx, &B.n_points, S)); CKC(dalloc(ctx, &B.n_rings, S)); CKC(dalloc(ctx, &B.ring_start, S * (R + 1))); CKC(dalloc(ctx, &B.status, S));
+    CKC(dalloc(ctx, &B.pts, S * N)); CKC(dalloc(ctx, &B.sorted, S * N));
+    CKC(dalloc(ctx, &B.cell_start, S * R * (VELO_AZ_BINS + 1))); CKC(dalloc(ctx, &B.sec_elev, S * R * VELO_SECTORS));
+    CKC(dalloc(ctx, &B.proj, S * C * N)); CKC(dalloc(ctx, &B.valid, S * C * N)); CKC(dalloc(ctx, &B.proj_count, S * C * R));
+    const size_t SK = S * VELO_NUM_KP_SETS * C;
+    CKC(dalloc(ctx, &B.kp, SK * F)); CKC(dalloc(ctx, &B.n_kp, SK)); CKC(dalloc(ctx, &B.has_depth, SK * F)); CKC(dalloc(ctx, &B.kpwd, SK * F));
+    CKC(dalloc(ctx, &B.n_hits, SK)); CKC(dalloc(ctx, &B.hit_tmp, SK * F)); CKC(dalloc(ctx, &B.kpwd_tmp, SK * F));
+    CKC(dalloc(ctx, &B.matches, S * C * MM * 2)); CKC(dalloc(ctx, &B.n_matches, S * C));
+    // units / normal equations
+    ctx->icp_partial_ctas = 296;
+    const size_t n_icp_units = S * P, n_vis_units = S * (size_t)(prm->f2f_iterations > 0 ? prm->f2f_iterations : 1);
+    CKC(cudaMallocHost((void **)&ctx->h_icp_units, n_icp_units * sizeof(IcpUnit)));
+    CKC(cudaMallocHost((void **)&ctx->h_vis_units, n_vis_units * sizeof(VisUnit)));
+    CKC(dalloc(ctx, &ctx->d_icp_units, n_icp_units)); CKC(dalloc(ctx, &ctx->d_vis_units, n_vis_units));
+    size_t part = n_icp_units * 8; if (part < (size_t)ctx->icp_partial_ctas) part = ctx->icp_partial_ctas;
+    CKC(dalloc(ctx, &ctx->d_icp_partial, part * 64)); CKC(dalloc(ctx, &ctx->d_icp_out, n_icp_units * VELO_NEQ_STRIDE));
+    ctx->vis_ctas = 0;
+    size_t vpart = n_vis_units * 4; if (vpart < 64) vpart = 64;
+    CKC(dalloc(ctx, &ctx->d_vis_partial, vpart * 64)); CKC(dalloc(ctx, &ctx->d_vis_out, n_vis_units * VELO_NEQ_STRIDE));
+    CKC(dalloc(ctx, &ctx->d_corr, N)); CKC(dalloc(ctx, &ctx->d_mout, C * MM));
+    CKC(dalloc(ctx, &ctx->d_lm_valid, C * MM)); CKC(dalloc(ctx, &ctx->d_lm_xyz, C * MM));
+    ctx->h_npoints.assign(S, 0);
+    // calibration for the device
+    DevCalib &d = ctx->dcal; memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 12; i++) d.vtc[i] = cal->velo_to_cam[i];
+    for (int c = 0; c < VELO_MAX_CAMS; c++) {
+        for (int i = 0; i < 3; i++) d.cam_t[c][i] = cal->cam_trans[c][i];
+        d.fov[c][0] = ceil_to_float(cal->min_x[c]); d.fov[c][1] = ceil_to_float(cal->max_x[c]);
+        d.fov[c][2] = ceil_to_float(cal->min_y[c]); d.fov[c][3] = ceil_to_float(cal->max_y[c]);
+    }
+    d.assoc_thr = ceil_to_float(prm->depth_assoc_thresh); d.abs_truncates = prm->abs_truncates; d.num_cams = prm->num_cams;
+    CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+    *out = ctx;
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
+    if (!ctx) return VELO_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->h_icp_units) cudaFreeHost(ctx->h_icp_units);
+    if (ctx->h_vis_units) cudaFreeHost(ctx->h_vis_units);
+    for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VELO_OK;
+}
+
+extern "C" const char *velo_gpu_last_error(const velo_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int velo_gpu_sync(velo_gpu_ctx *ctx) { if (!ctx) return VELO_ERR_INVALID_ARG; CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaGetLastError()); return VELO_OK; }
+extern "C" int velo_gpu_device_name(velo_gpu_ctx *ctx, char *buf, int n) {
+    if (!ctx || !buf || n < 1) return VELO_ERR_INVALID_ARG;
+    cudaDeviceProp dp; CK(cudaGetDeviceProperties(&dp, ctx->device));
+    snprintf(buf, n, "%s", dp.name); return VELO_OK;
+}
+extern "C" int velo_gpu_host_alloc(void **p, uint64_t bytes) { if (!p) return VELO_ERR_INVALID_ARG; return cudaMallocHost(p, bytes ? bytes : 1) == cudaSuccess ? VELO_OK : VELO_ERR_CUDA; }
+extern "C" int velo_gpu_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? VELO_OK : VELO_ERR_CUDA; }
+extern "C" int velo_gpu_timer_begin(velo_gpu_ctx *ctx) { if (!ctx) return VELO_ERR_INVALID_ARG; CK(cudaSetDevice(ctx->device)); CK(cudaEventRecord(ctx->t0, ctx->stream)); return VELO_OK; }
+extern "C" int velo_gpu_timer_end(velo_gpu_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return VELO_ERR_INVALID_ARG;
+    CK(cudaEventRecord(ctx->t1, ctx->stream)); CK(cudaEventSynchronize(ctx->t1)); CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return VELO_OK;
+}
+extern "C" int velo_gpu_profile_enable(velo_gpu_ctx *ctx, int on) { if (!ctx) return VELO_ERR_INVALID_ARG; ctx->profile = on != 0; return VELO_OK; }
+extern "C" int velo_gpu_profile_reset(velo_gpu_ctx *ctx) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->recs) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->recs.clear();
+    return VELO_OK;
+}
+extern "C" int velo_gpu_profile_read(velo_gpu_ctx *ctx, float ms[VELO_NUM_KERNELS], int launches[VELO_NUM_KERNELS]) {
+    if (!ctx || !ms || !launches) return VELO_ERR_INVALID_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < VELO_NUM_KERNELS; i++) { ms[i] = 0.f; launches[i] = 0; }
+    for (auto &r : ctx->recs) { float t = 0.f; CK(cudaEventElapsedTime(&t, r.a, r.b)); ms[r.k] += t; launches[r.k]++; }
+    return VELO_OK;
+}
+extern "C" int velo_gpu_launch_count(velo_gpu_ctx *ctx, int64_t *n) { if (!ctx || !n) return VELO_ERR_INVALID_ARG; *n = ctx->launches; return VELO_OK; }
+
+static int check_slot(velo_gpu_ctx *ctx, int slot) { return (slot >= 0 && slot < ctx->B.S) ? VELO_OK : fail(ctx, VELO_ERR_INVALID_ARG, "slot out of range"); }
+static int check_cam(velo_gpu_ctx *ctx, int cam) { return (cam >= 0 && cam < ctx->B.C) ? VELO_OK : fail(ctx, VELO_ERR_INVALID_ARG, "camera out of range"); }
+static int slot_status(velo_gpu_ctx *ctx, int slot) {
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, ctx->B.status + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st != 0) return fail(ctx, st, "scan has more rings than max_rings (kitti.h:166-173 ring count is data dependent)");
+    return VELO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single-frame path
+extern "C" int velo_gpu_scan_upload(velo_gpu_ctx *ctx, int slot, const float *xyzr, int n) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot)) return VELO_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && !xyzr)) return fail(ctx, VELO_ERR_INVALID_ARG, "bad scan pointer / size");
+    if (n > ctx->prm.max_points) return fail(ctx, VELO_ERR_CAPACITY, "scan has more points than max_points");
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    if (n > 0) CK(cudaMemcpyAsync(B.raw + (size_t)slot * B.N, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.n_points + slot, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // &n is a stack variable
+    ctx->h_npoints[slot] = n;
+    Launcher L = launcher(ctx);
+    launch_ingest(L, B, ctx->dcal, slot, 1);
+    launch_index(L, B, ctx->dcal, slot, 1);
+    CK(cudaGetLastError());
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_scan_info(velo_gpu_ctx *ctx, int slot, int *n_points, int *n_rings) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int st = slot_status(ctx, slot); if (st) return st;
+    int np = 0, nr = 0;
+    CK(cudaMemcpyAsync(&np, ctx->B.n_points + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&nr, ctx->B.n_rings + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_points) *n_points = np;
+    if (n_rings) *n_rings = nr;
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_scan_download(velo_gpu_ctx *ctx, int slot, float *xyz1, int *ring_start) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    int np, nr; int st = velo_gpu_scan_info(ctx, slot, &np, &nr); if (st) return st;
+    const DevBuffers &B = ctx->B;
+    if (xyz1 && np > 0) CK(cudaMemcpyAsync(xyz1, B.pts + (size_t)slot * B.N, (size_t)np * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ring_start) CK(cudaMemcpyAsync(ring_start, B.ring_start + (size_t)slot * (B.R + 1), (size_t)(nr + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ring_start && nr == 0) ring_start[0] = 0;
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_project(velo_gpu_ctx *ctx, int slot, int cam) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot) || check_cam(ctx, cam)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // the projection kernel handles all cameras of the rig in one pass over the scan (main.cpp:254-256 projects per camera)
+    launch_project(launcher(ctx), ctx->B, ctx->dcal, slot, 1);
+    CK(cudaGetLastError());
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_project_download(velo_gpu_ctx *ctx, int slot, int cam, int *ring_count, float *proj, float *valid, int *total) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_cam(ctx, cam)) return VELO_ERR_INVALID_ARG;
+    int np, nr; int st = velo_gpu_scan_info(ctx, slot, &np, &nr); if (st) return st;
+    const DevBuffers &B = ctx->B;
+    std::vector<int> rc(nr + 1, 0), rs(nr + 1, 0);
+    if (nr > 0) {
+        CK(cudaMemcpyAsync(rc.data(), B.proj_count + ((size_t)slot * B.C + cam) * B.R, nr * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(rs.data(), B.ring_start + (size_t)slot * (B.R + 1), (nr + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    int o = 0;
+    for (int s = 0; s < nr; s++) {
+        if (ring_count) ring_count[s] = rc[s];
+        if (rc[s] > 0) {
+            if (proj) CK(cudaMemcpyAsync(proj + 2 * (size_t)o, B.proj + ((size_t)slot * B.C + cam) * B.N + rs[s], rc[s] * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+            if (valid) CK(cudaMemcpyAsync(valid + 4 * (size_t)o, B.valid + ((size_t)slot * B.C + cam) * B.N + rs[s], rc[s] * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        o += rc[s];
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (total) *total = o;
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int set, const float *kp, int F, int *has_depth, float *kpwd, int *n_hits) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot) || check_cam(ctx, cam)) return VELO_ERR_INVALID_ARG;
+    if (set < 0 || set >= VELO_NUM_KP_SETS || F < 0 || (F > 0 && !kp)) return fail(ctx, VELO_ERR_INVALID_ARG, "bad keypoint set / pointer");
+    if (F > ctx->B.F) return fail(ctx, VELO_ERR_CAPACITY, "more keypoints than max_features");
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + set) * B.C + cam;
+    if (F > 0) CK(cudaMemcpyAsync(B.kp + sc * B.F, kp, (size_t)F * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.n_kp + sc, &F, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    launch_assoc(launcher(ctx), B, ctx->dcal, slot, 1, set, 1, cam, 1);
+    CK(cudaGetLastError());
+    int nh = 0;
+    CK(cudaMemcpyAsync(&nh, B.n_hits + sc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (has_depth && F > 0) CK(cudaMemcpyAsync(has_depth, B.has_depth + sc * B.F, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (kpwd && nh > 0) { CK(cudaMemcpyAsync(kpwd, B.kpwd + sc * B.F, (size_t)nh * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    if (n_hits) *n_hits = nh;
+    return VELO_OK;
+}
+
+static void fill_icp_unit(const velo_gpu_ctx *ctx, IcpUnit *u, int src, int tgt, const double pose[6], int iter, int skip) {
+    memset(u, 0, sizeof(*u));
+    u->src_slot = src; u->tgt_slot = tgt; u->iter = iter; u->skip = skip;
+    const double thr = ctx->prm.correspondence_thresh_icp / iter / iter / iter / iter;     // velo.h:829
+    u->thr_f = floor_to_float(thr);
+    u->norm_thr_f = ceil_to_float(ctx->prm.icp_norm_condition);                            // velo.h:873
+    u->loss_a = ctx->prm.loss_thresh_3DPD; u->weight = ctx->prm.weight_3DPD;               // velo.h:885-891
+    make_pose_pack(pose, &u->pose);
+}
+static int auto_ctas(const velo_gpu_ctx *ctx, int n_units, int cap) {
+    int c = ctx->prm.ctas_per_icp_unit;
+    if (c <= 0) { c = (148 * 12 + n_units - 1) / n_units; if (c < 8) c = 8; }
+    if (c > cap) c = cap;
+    return c < 1 ? 1 : c;
+}
+
+extern "C" int velo_gpu_icp_pass(velo_gpu_ctx *ctx, int slot_M, int slot_S, const double pose[6], int iter, int icp_skip,
+                                 velo_icp_corr *corr, int corr_capacity, int *n_queries, int *n_kept, double *neq) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot_M) || check_slot(ctx, slot_S)) return VELO_ERR_INVALID_ARG;
+    if (!pose || iter < 1 || icp_skip < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "bad pose / iter / icp_skip");
+    CK(cudaSetDevice(ctx->device));
+    int st = slot_status(ctx, slot_M); if (st) return st;
+    st = slot_status(ctx, slot_S); if (st) return st;
+    fill_icp_unit(ctx, &ctx->h_icp_units[0], slot_M, slot_S, pose, iter, icp_skip);
+    CK(cudaMemcpyAsync(ctx->d_icp_units, ctx->h_icp_units, sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+    const int ctas = auto_ctas(ctx, 1, ctx->icp_partial_ctas);
+    if (corr) CK(cudaMemsetAsync(ctx->d_corr, 0, (size_t)ctx->B.N * sizeof(velo_icp_corr), ctx->stream));
+    launch_icp(launcher(ctx), ctx->B, ctx->dcal, ctx->d_icp_units, 1, ctas, ctx->d_icp_partial, ctx->d_icp_out, corr ? ctx->d_corr : nullptr);
+    CK(cudaGetLastError());
+    double out[VELO_NEQ_STRIDE];
+    CK(cudaMemcpyAsync(out, ctx->d_icp_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int nq = (int)out[58];
+    if (corr) {
+        if (nq > corr_capacity) return fail(ctx, VELO_ERR_CAPACITY, "corr_capacity smaller than the number of queries");
+        if (nq > 0) CK(cudaMemcpyAsync(corr, ctx->d_corr, (size_t)nq * sizeof(velo_icp_corr), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_queries) *n_queries = nq;
+    if (n_kept) *n_kept = (int)out[56];
+    if (neq) memcpy(neq, out, sizeof(out));
+    return VELO_OK;
+}
+
+static VisTun vis_tun(const velo_gpu_ctx *ctx) {
+    const velo_gpu_params &p = ctx->prm;
+    return VisTun{ p.weight_3D2D, p.weight_2D2D, p.loss_thresh_3D2D, p.loss_thresh_2D2D, p.loss_thresh_3D3D, p.outlier_reject,
+                   p.enable_2d2d, p.enable_3d2d, p.abs_truncates, 0 };
+}
+
+extern "C" int velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1, int slot2, int set2, const int *n_matches, const int *matches,
+                                         const int *lm_valid, const float *lm_xyz, const double pose[6], int iter,
+                                         velo_vis_block *blocks, int block_capacity, int *n_blocks, double *neq) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot1) || check_slot(ctx, slot2)) return VELO_ERR_INVALID_ARG;
+    if (!n_matches || !pose || iter < 1 || set1 < 0 || set1 >= VELO_NUM_KP_SETS || set2 < 0 || set2 >= VELO_NUM_KP_SETS)
+        return fail(ctx, VELO_ERR_INVALID_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const int C = B.C, MM = B.MM;
+    int tot = 0;
+    for (int c = 0; c < C; c++) { if (n_matches[c] < 0 || n_matches[c] > MM) return fail(ctx, VELO_ERR_CAPACITY, "more matches than max_matches"); tot += n_matches[c]; }
+    if (tot > 0 && !matches) return fail(ctx, VELO_ERR_INVALID_ARG, "null matches");
+    // matches arrive concatenated per camera; the device layout is [cam][MM]
+    int off = 0;
+    for (int c = 0; c < C; c++) {
+        if (n_matches[c] > 0) {
+            CK(cudaMemcpyAsync(B.matches + 2 * (((size_t)slot1 * C + c) * MM), matches + 2 * (size_t)off, (size_t)n_matches[c] * 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            if (lm_valid) {
+                CK(cudaMemcpyAsync(ctx->d_lm_valid + (size_t)c * MM, lm_valid + off, (size_t)n_matches[c] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->d_lm_xyz + (size_t)c * MM, lm_xyz + 4 * (size_t)off, (size_t)n_matches[c] * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
+        off += n_matches[c];
+    }
+    CK(cudaMemcpyAsync(B.n_matches + (size_t)slot1 * C, n_matches, C * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    VisUnit *u = &ctx->h_vis_units[0];
+    memset(u, 0, sizeof(*u));
+    u->slot1 = slot1; u->set1 = set1; u->slot2 = slot2; u->set2 = set2; u->iter = iter;
+    memcpy(u->pose, pose, 6 * sizeof(double));
+    CK(cudaMemcpyAsync(ctx->d_vis_units, u, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_mout, 0, (size_t)C * MM * sizeof(VisMatchOut), ctx->stream));
+    const int ctas = 32;
+    launch_visual(launcher(ctx), B, ctx->dcal, ctx->d_vis_units, 1, vis_tun(ctx), lm_valid ? ctx->d_lm_valid : nullptr, lm_valid ? ctx->d_lm_xyz : nullptr,
+                  ctx->d_vis_partial, ctx->d_vis_out, ctx->d_mout, ctas);
+    CK(cudaGetLastError());
+    double out[VELO_NEQ_STRIDE];
+    CK(cudaMemcpyAsync(out, ctx->d_vis_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<VisMatchOut> mo((size_t)C * MM);
+    CK(cudaMemcpyAsync(mo.data(), ctx->d_mout, mo.size() * sizeof(VisMatchOut), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // residualStats order: camera-major, match order, block order (velo.h:934-976)
+    int nb = 0;
+    for (int c = 0; c < C; c++) for (int i = 0; i < n_matches[c]; i++) {
+        const VisMatchOut &m = mo[(size_t)c * MM + i];
+        for (int b = 0; b < m.n; b++) { if (blocks && nb < block_capacity) blocks[nb] = m.b[b]; nb++; }
+    }
+    if (blocks && nb > block_capacity) return fail(ctx, VELO_ERR_CAPACITY, "block_capacity too small");
+    if (n_blocks) *n_blocks = nb;
+    if (neq) memcpy(neq, out, sizeof(out));
+    return VELO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batched path
+static int check_range(velo_gpu_ctx *ctx, int slot0, int count) {
+    if (slot0 < 0 || count < 1 || slot0 + count > ctx->B.S) return fail(ctx, VELO_ERR_INVALID_ARG, "slot range out of bounds");
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in) {
+    if (!ctx || !in) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const size_t C = B.C, F = B.F, MM = B.MM;
+    if (in->scans && in->n_points) {
+        for (int i = 0; i < count; i++) if (in->n_points[i] < 0 || in->n_points[i] > ctx->prm.max_points) return fail(ctx, VELO_ERR_CAPACITY, "scan has more points than max_points");
+        CK(cudaMemcpy2DAsync(B.raw + (size_t)slot0 * B.N, (size_t)B.N * sizeof(float4), in->scans, (size_t)ctx->prm.max_points * sizeof(float4),
+                             (size_t)ctx->prm.max_points * sizeof(float4), count, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.n_points + slot0, in->n_points, count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        for (int i = 0; i < count; i++) ctx->h_npoints[slot0 + i] = in->n_points[i];
+    }
+    if (in->kp && in->n_kp) {
+        const size_t per = VELO_NUM_KP_SETS * C;
+        for (size_t i = 0; i < count * per; i++) if (in->n_kp[i] < 0 || in->n_kp[i] > (int)F) return fail(ctx, VELO_ERR_CAPACITY, "more keypoints than max_features");
+        CK(cudaMemcpyAsync(B.kp + (size_t)slot0 * per * F, in->kp, count * per * F * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.n_kp + (size_t)slot0 * per, in->n_kp, count * per * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (in->matches && in->n_matches) {
+        for (size_t i = 0; i < count * C; i++) if (in->n_matches[i] < 0 || in->n_matches[i] > (int)MM) return fail(ctx, VELO_ERR_CAPACITY, "more matches than max_matches");
+        CK(cudaMemcpyAsync(B.matches + (size_t)slot0 * C * MM * 2, in->matches, count * C * MM * 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.n_matches + (size_t)slot0 * C, in->n_matches, count * C * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (in->icp_poses && in->pass_iter) {
+        if (in->n_passes < 1 || in->n_passes > B.P) return fail(ctx, VELO_ERR_CAPACITY, "n_passes exceeds max_icp_passes");
+        ctx->batch_passes = in->n_passes;
+        for (int i = 0; i < count; i++) for (int p = 0; p < in->n_passes; p++) {
+            const int slot = slot0 + i;
+            IcpUnit *u = &ctx->h_icp_units[(size_t)slot * B.P + p];
+            if (in->pass_iter[p] < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "pass_iter must be >= 1");
+            fill_icp_unit(ctx, u, slot, slot - 1, in->icp_poses + 6 * ((size_t)i * in->n_passes + p), in->pass_iter[p], ctx->prm.icp_skip);
+            if (slot == 0) u->src_slot = -1;
+        }
+        CK(cudaMemcpyAsync(ctx->d_icp_units + (size_t)slot0 * B.P, ctx->h_icp_units + (size_t)slot0 * B.P, (size_t)count * B.P * sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (in->vis_poses) {
+        const int V = ctx->prm.f2f_iterations;
+        if (in->n_vis_iters < 1 || in->n_vis_iters > V) return fail(ctx, VELO_ERR_CAPACITY, "n_vis_iters exceeds f2f_iterations");
+        ctx->batch_vis = in->n_vis_iters;
+        for (int i = 0; i < count; i++) for (int it = 0; it < in->n_vis_iters; it++) {
+            const int slot = slot0 + i;
+            VisUnit *u = &ctx->h_vis_units[(size_t)slot * V + it];
+            memset(u, 0, sizeof(*u));
+            // frame1 = current slot, tracked set (1); frame2 = previous slot, detected set (0)  (main.cpp:388-405, velo.h:609-610)
+            u->slot1 = slot; u->set1 = 1; u->slot2 = slot - 1; u->set2 = 0; u->iter = it + 1;
+            memcpy(u->pose, in->vis_poses + 6 * ((size_t)i * in->n_vis_iters + it), 6 * sizeof(double));
+        }
+        CK(cudaMemcpyAsync(ctx->d_vis_units + (size_t)slot0 * V, ctx->h_vis_units + (size_t)slot0 * V, (size_t)count * V * sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int first_has_prev) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    Launcher L = launcher(ctx);
+    if (stages & VELO_STAGE_INGEST) launch_ingest(L, B, ctx->dcal, slot0, count);
+    if (stages & VELO_STAGE_INDEX) launch_index(L, B, ctx->dcal, slot0, count);
+    if (stages & VELO_STAGE_PROJECT) launch_project(L, B, ctx->dcal, slot0, count);
+    if (stages & VELO_STAGE_ASSOC) launch_assoc(L, B, ctx->dcal, slot0, count, 0, VELO_NUM_KP_SETS, 0, B.C);
+    const int skip_first = (first_has_prev && slot0 > 0) ? 0 : 1;
+    const int pairs = count - skip_first, s_first = slot0 + skip_first;
+    if ((stages & VELO_STAGE_ICP) && pairs > 0 && ctx->batch_passes > 0) {
+        if (ctx->batch_passes != B.P) return fail(ctx, VELO_ERR_STATE, "batched ICP needs n_passes == max_icp_passes (dense unit layout)");
+        const int n_units = pairs * B.P;
+        const int ctas = auto_ctas(ctx, n_units, 8);
+        if (skip_first) CK(cudaMemsetAsync(ctx->d_icp_out + (size_t)slot0 * B.P * VELO_NEQ_STRIDE, 0, (size_t)B.P * VELO_NEQ_STRIDE * sizeof(double), ctx->stream));
+        launch_icp(L, B, ctx->dcal, ctx->d_icp_units + (size_t)s_first * B.P, n_units, ctas, ctx->d_icp_partial,
+                   ctx->d_icp_out + (size_t)s_first * B.P * VELO_NEQ_STRIDE, nullptr);
+    }
+    if ((stages & VELO_STAGE_VISUAL) && pairs > 0 && ctx->batch_vis > 0) {
+        const int V = ctx->prm.f2f_iterations;
+        if (ctx->batch_vis != V) return fail(ctx, VELO_ERR_STATE, "batched visual stage needs n_vis_iters == f2f_iterations");
+        const int n_units = pairs * V;
+        if (skip_first) CK(cudaMemsetAsync(ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, 0, (size_t)V * VELO_NEQ_STRIDE * sizeof(double), ctx->stream));
+        launch_visual(L, B, ctx->dcal, ctx->d_vis_units + (size_t)s_first * V, n_units, vis_tun(ctx), nullptr, nullptr, ctx->d_vis_partial,
+                      ctx->d_vis_out + (size_t)s_first * V * VELO_NEQ_STRIDE, nullptr, 4);
+    }
+    CK(cudaGetLastError());
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *icp_neq, double *vis_neq, int *has_depth, int *n_hits) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const size_t per = VELO_NUM_KP_SETS * (size_t)B.C;
+    const int V = ctx->prm.f2f_iterations;
+    if (icp_neq) CK(cudaMemcpyAsync(icp_neq, ctx->d_icp_out + (size_t)slot0 * B.P * VELO_NEQ_STRIDE, (size_t)count * B.P * VELO_NEQ_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (vis_neq) CK(cudaMemcpyAsync(vis_neq, ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, (size_t)count * V * VELO_NEQ_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (has_depth) CK(cudaMemcpyAsync(has_depth, B.has_depth + (size_t)slot0 * per * B.F, (size_t)count * per * B.F * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_hits) CK(cudaMemcpyAsync(n_hits, B.n_hits + (size_t)slot0 * per, (size_t)count * per * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_batch_counts(velo_gpu_ctx *ctx, int slot0, int count, int *n_points, int *n_rings, int *proj_total, int *status) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    std::vector<int> nr(count), pc((size_t)count * B.C * B.R);
+    CK(cudaMemcpyAsync(nr.data(), B.n_rings + slot0, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pc.data(), B.proj_count + (size_t)slot0 * B.C * B.R, pc.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_points) CK(cudaMemcpyAsync(n_points, B.n_points + slot0, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(status, B.status + slot0, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < count; i++) {
+        if (n_rings) n_rings[i] = nr[i];
+        if (proj_total) for (int c = 0; c < B.C; c++) {
+            int t = 0;
+            for (int s = 0; s < nr[i]; s++) t += pc[((size_t)i * B.C + c) * B.R + s];
+            proj_total[(size_t)i * B.C + c] = t;
+        }
+    }
+    return VELO_OK;
+}

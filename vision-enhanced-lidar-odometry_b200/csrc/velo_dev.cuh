@@ -1,0 +1,104 @@
+// velo_dev.cuh — device-side data layout and kernel launchers of the B200-native VELO front end.
+//
+// Layout in HBM (one context = one GPU).  S = max_slots, N = max_points (padded to 128), R = max_rings,
+// C = num_cams, F = max_features, MM = max_matches.  Everything is a dense [slot][...] array so that one
+// launch covers a whole batch of frames (grid.y / grid.z = slot):
+//   raw        float4 [S][N]          KITTI {x,y,z,reflectance} as uploaded            (kitti.h:121-152)
+//   flagbits   u32    [S][N/32]       ring-boundary flags (kitti.h:166)
+//   ring_start int    [S][R+1]        ring r = pts[ring_start[r] .. ring_start[r+1])
+//   pts        float4 [S][N]          ring-ordered cam-0 frame {x,y,z,1}               (kitti.h:154-185)
+//   sorted     float4 [S][N]          per ring counting-sorted by azimuth bin, .w = index in ring (int bits)
+//   cell_start int    [S][R][AZ+1]    start of (ring, azimuth bin) in `sorted` (slot-relative)
+//   sec_elev   float2 [S][R][SEC]     elevation interval of the ring inside one azimuth sector (AZ/SEC bins)
+//   proj       float2 [S][C][N]       canonical projection, ring r at offset ring_start[r] (velo.h:366)
+//   valid      float4 [S][C][N]       matching cam-0 points (velo.h:368)
+//   proj_count int    [S][C][R]
+//   kp         float2 [S][2][C][F]    keypoints (set 0 = detected, set 1 = tracked)
+//   has_depth  int    [S][2][C][F],  kpwd float4 [S][2][C][F],  n_hits int [S][2][C]   (velo.h:377-497)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "velo_gpu.h"
+
+#define VELO_AZ_BINS 512
+#define VELO_SECTORS 64
+#define VELO_BINS_PER_SECTOR (VELO_AZ_BINS / VELO_SECTORS)
+#define VELO_MAX_RINGS_HARD 256
+#define VELO_IDX_BITS 20            /* index-in-ring bits of the neighbour key */
+#define VELO_RING_BITS 12
+
+enum {
+    VK_INGEST_FLAGS = 0, VK_INGEST_RINGS, VK_INGEST_PERMUTE, VK_INDEX_BUILD, VK_PROJECT, VK_ASSOC_SEARCH,
+    VK_ASSOC_COMPACT, VK_ICP_PASS, VK_NEQ_REDUCE, VK_VISUAL, VK_MISC0, VK_MISC1
+};
+
+// calibration packed for kernel parameters
+struct DevCalib {
+    float vtc[12];            // velo_to_cam rows 0..2 (kitti.h:100-105)
+    float cam_t[VELO_MAX_CAMS][3];
+    float fov[VELO_MAX_CAMS][4];   // min_x, max_x, min_y, max_y as the equivalent float thresholds (hazard H3)
+    float assoc_thr;          // float equivalent of `(double)|dx| < depth_assoc_thresh`
+    int   abs_truncates;
+    int   num_cams;
+};
+
+struct DevBuffers {
+    int S, N, R, C, F, MM, P;
+    float4 *raw; uint32_t *flagbits; int *n_points; int *n_rings; int *ring_start; int *status;
+    float4 *pts; float4 *sorted; int *cell_start; float2 *sec_elev;
+    float2 *proj; float4 *valid; int *proj_count;
+    float2 *kp; int *n_kp; int *has_depth; float4 *kpwd; int *n_hits; int *hit_tmp; float4 *kpwd_tmp;
+    int *matches; int *n_matches;
+};
+
+// pose-dependent constants computed once on the host with the host libm (hazard H8)
+struct PosePack {
+    double w[3], t[3];        // angle-axis, translation
+    double c, s;              // cos(theta), sin(theta)
+    double u[3];              // w / theta
+    double dR[27];            // dR[k][i][j] = d (R(w) e_j)_i / d w_k  (forward-mode, same branch as the rotation)
+    int small_angle;          // theta^2 <= DBL_EPSILON branch of AngleAxisRotatePoint
+    int pad;
+};
+
+struct IcpUnit {
+    int src_slot, tgt_slot;
+    int iter, skip;
+    float thr_f;              // largest float f with (double)f <= correspondence_thresh_icp/iter^4 (velo.h:829)
+    float norm_thr_f;         // smallest float f with (double)f >= icp_norm_condition (velo.h:873)
+    double loss_a;            // loss_thresh_3DPD
+    double weight;            // weight_3DPD
+    PosePack pose;
+};
+
+struct VisUnit {
+    int slot1, set1, slot2, set2;
+    int iter, pad;
+    double pose[6];
+};
+
+struct VisTun {
+    double w3d2d, w2d2d, l3d2d, l2d2d, l3d3d, outlier;
+    int en2d2d, en3d2d, abs_trunc, pad;
+};
+
+// per-match parity record of the visual kernel: up to 3 blocks
+struct VisMatchOut { int n; int pad; velo_vis_block b[3]; };
+
+struct Launcher {
+    cudaStream_t stream;
+    // profiling hook: called before/after each launch with the kernel class
+    void (*pre)(void *user, int k);
+    void (*post)(void *user, int k);
+    void *user;
+};
+
+void launch_ingest(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
+void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
+void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
+void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams);
+// units: device array [n_units]; partial: [n_units][ctas][64] doubles; out: [n_units][VELO_NEQ_STRIDE]; corr optional (single unit)
+void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int ctas,
+                double *partial, double *out, velo_icp_corr *corr);
+void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
+                   const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas);

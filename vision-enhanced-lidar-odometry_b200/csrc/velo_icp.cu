@@ -1,0 +1,269 @@
+// velo_icp.cu — stages 3+4 for the lidar term: transform_point (utility.h:97-103), the per-ring 1-NN / top-2 ring /
+// third-point / normal logic of velo.h:806-874, cost3DPD residual + Jacobian (costfunctions.h:17-58) and the 6x6
+// normal equations (velo.h:885-902), fused in one kernel.
+//
+// The reference asks 64 kd-trees for one nearest neighbour each and then keeps the two best rings.  That is
+// equivalent to: over all target points within the distance threshold, ordered by the key (d2, ring, index),
+//     i = the smallest key,        j = the smallest key whose ring differs from ring(i).
+// (d2 as f32 bits orders like the value; ties go to the lower ring, then the lower point index — hazards H9 and the
+// north-star tie rule.)  A min over keys is order independent, so any exhaustive enumeration gives bit-identical
+// indices.  The enumeration is pruned, conservatively, with the ring x azimuth organisation of the scan:
+// a ring can only contain a closer point if its elevation interval comes within asin(b/|q|) of the query and
+// only inside the azimuth window asin(b/|q_xy|), b = current bound on sqrt(d2_j).
+#include "velo_common.cuh"
+
+#define ICP_THREADS 256
+#define KEY_INF 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ u64 make_key(float d2, int ring, int idx) {
+    return ((u64)__float_as_uint(d2) << 32) | (u64)(((unsigned)ring << VELO_IDX_BITS) | (unsigned)idx);
+}
+__device__ __forceinline__ int key_ring(u64 k) { return (int)(((unsigned)k) >> VELO_IDX_BITS); }
+__device__ __forceinline__ int key_idx(u64 k) { return (int)(((unsigned)k) & ((1u << VELO_IDX_BITS) - 1u)); }
+__device__ __forceinline__ float key_d2(u64 k) { return __uint_as_float((unsigned)(k >> 32)); }
+
+// best two rings under re-visits of the same ring
+__device__ __forceinline__ void merge_key(u64 k, u64 &ki, u64 &kj) {
+    if (k == KEY_INF) return;
+    const int r = key_ring(k);
+    if (r == key_ring(ki)) { if (k < ki) ki = k; }
+    else if (r == key_ring(kj)) { if (k < kj) kj = k; if (kj < ki) { u64 t = ki; ki = kj; kj = t; } }
+    else if (k < ki) { kj = ki; ki = k; }
+    else if (k < kj) kj = k;
+}
+
+struct Window { int b0, b1; bool wrapped, full; float gam; };
+
+// azimuth window / elevation tolerance for bound d2b around a query with azimuth az, xy-range D, range rho
+__device__ __forceinline__ Window make_window(float d2b, float az, float D, float rho) {
+    Window w;
+    const float b = sqrtf(d2b) * (1.0f + 1e-5f) + 1e-6f;
+    w.gam = (b < rho) ? asinf(b / rho) + 2e-5f : 4.0f;
+    w.full = !(b < D); w.wrapped = false; w.b0 = 0; w.b1 = VELO_AZ_BINS - 1;
+    if (!w.full) {
+        const float h = asinf(b / D) + 2e-5f;
+        float lo = az - h, hi = az + h;
+        if (h >= CUDART_PI_F) { w.full = true; }
+        else if (lo < -CUDART_PI_F) { w.b0 = az_bin(lo + 2.0f * CUDART_PI_F); w.b1 = az_bin(hi); w.wrapped = true; }
+        else if (hi > CUDART_PI_F) { w.b0 = az_bin(lo); w.b1 = az_bin(hi - 2.0f * CUDART_PI_F); w.wrapped = true; }
+        else { w.b0 = az_bin(lo); w.b1 = az_bin(hi); }
+        if (w.wrapped && w.b0 <= w.b1 + 1) { w.full = true; w.wrapped = false; w.b0 = 0; w.b1 = VELO_AZ_BINS - 1; }
+    }
+    return w;
+}
+
+// min key over sorted[start, end) of ring s
+__device__ __forceinline__ u64 scan_range(const float4 *__restrict__ sorted, int start, int end, int s, float mx, float my, float mz, float thr_f, u64 best) {
+#pragma unroll 4
+    for (int p = start; p < end; p++) {
+        const float4 c = __ldg(sorted + p);
+        const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
+        if (d2 <= thr_f) { const u64 k = make_key(d2, s, __float_as_int(c.w)); if (k < best) best = k; }
+    }
+    return best;
+}
+__device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, const int *__restrict__ cs, int s, const Window &w,
+                                         float mx, float my, float mz, float thr_f) {
+    u64 best = KEY_INF;
+    if (!w.wrapped) best = scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), s, mx, my, mz, thr_f, best);
+    else {
+        best = scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), s, mx, my, mz, thr_f, best);
+        best = scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), s, mx, my, mz, thr_f, best);
+    }
+    return best;
+}
+// elevation gap between el and the ring's interval over the sectors touched by the window
+__device__ __forceinline__ float ring_gap(const float2 *__restrict__ se, const Window &w, float el) {
+    float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+    int sa = w.b0 / VELO_BINS_PER_SECTOR, sb = w.b1 / VELO_BINS_PER_SECTOR;
+    if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
+    for (int sec = sa;; sec = (sec + 1) & (VELO_SECTORS - 1)) {
+        const float2 e = __ldg(se + sec);
+        lo = fminf(lo, e.x); hi = fmaxf(hi, e.y);
+        if (sec == sb) break;
+    }
+    return fmaxf(fmaxf(lo - el, el - hi), 0.0f);   // +inf when the sectors are empty
+}
+
+// grid = (ctas per unit, n_units); one thread = one query at a time
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
+                                                          double *__restrict__ partial, velo_icp_corr *__restrict__ corr) {
+    __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
+    __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
+    __shared__ double s_rows[ICP_THREADS / 32][32 * NEQ_ROW];
+    __shared__ double s_red[(ICP_THREADS / 32) * 56];
+    __shared__ int s_kept;
+    const IcpUnit &U = units[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (U.src_slot < 0) {   // unit without a previous scan: contributes nothing
+        if (tid < 59) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + tid] = 0.0;
+        return;
+    }
+    const int nrM = B.n_rings[U.src_slot], nrS = B.n_rings[U.tgt_slot];
+    const int *rsM = B.ring_start + (size_t)U.src_slot * (B.R + 1);
+    const int *rsS = B.ring_start + (size_t)U.tgt_slot * (B.R + 1);
+    const int skip = U.skip;
+    if (tid == 0) {
+        int q = 0; s_kept = 0;
+        for (int s = 0; s < nrM; s++) { s_q[s] = q; int r0 = rsM[s], L = rsM[s + 1] - r0; s_rsM[s] = r0; q += (L + skip - 1) / skip; }
+        s_q[nrM] = q;
+    }
+    __syncthreads();
+    const int Q = s_q[nrM];
+    const int per = (((Q + gridDim.x - 1) / gridDim.x) + 31) & ~31;
+    const int q0 = blockIdx.x * per, q1 = min(Q, q0 + per);
+    const float4 *ptsM = B.pts + (size_t)U.src_slot * B.N;
+    const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
+    const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
+    const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
+    const float2 *seS = B.sec_elev + (size_t)U.tgt_slot * B.R * VELO_SECTORS;
+    const PosePack &P = U.pose;
+    const float thr_f = U.thr_f;
+    double acc = 0.0, raw = 0.0;
+    int kept_local = 0;
+
+    for (int qb = q0; qb < q1; qb += ICP_THREADS) {
+        const int q = qb + tid;
+        bool kept = false;
+        double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
+        if (q < q1) {
+            // (sm, smi) of this query: velo.h:806-807
+            int lo = 0, hi = nrM - 1;
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_q[mid] <= q) lo = mid; else hi = mid - 1; }
+            const int sm = lo, smi = (q - s_q[sm]) * skip;
+            const float4 pm = __ldg(ptsM + s_rsM[sm] + smi);
+            // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
+            const double x0 = pm.x, x1 = pm.y, x2 = pm.z;
+            double y0, y1, y2;
+            if (!P.small_angle) {
+                const double c0 = __dsub_rn(__dmul_rn(P.u[1], x2), __dmul_rn(P.u[2], x1));
+                const double c1 = __dsub_rn(__dmul_rn(P.u[2], x0), __dmul_rn(P.u[0], x2));
+                const double c2 = __dsub_rn(__dmul_rn(P.u[0], x1), __dmul_rn(P.u[1], x0));
+                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.u[0], x0), __dmul_rn(P.u[1], x1)), __dmul_rn(P.u[2], x2));
+                const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.c));
+                y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.c), __dmul_rn(c0, P.s)), __dmul_rn(P.u[0], tmp));
+                y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.c), __dmul_rn(c1, P.s)), __dmul_rn(P.u[1], tmp));
+                y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.c), __dmul_rn(c2, P.s)), __dmul_rn(P.u[2], tmp));
+            } else {
+                y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.w[1], x2), __dmul_rn(P.w[2], x1)));
+                y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.w[2], x0), __dmul_rn(P.w[0], x2)));
+                y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.w[0], x1), __dmul_rn(P.w[1], x0)));
+            }
+            const float mx = __double2float_rn(__dadd_rn(y0, P.t[0]));
+            const float my = __double2float_rn(__dadd_rn(y1, P.t[1]));
+            const float mz = __double2float_rn(__dadd_rn(y2, P.t[2]));
+
+            // ---- pruning geometry of the query in the index frame of the target scan
+            float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
+            const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float az = atan2f(vy, vx), el = atan2f(vz, D);
+            const int bq = az_bin(az), secq = bq / VELO_BINS_PER_SECTOR;
+
+            u64 ki = KEY_INF, kj = KEY_INF;
+            // seeds: the two rings closest in elevation, 3 azimuth bins each -> a tight bound before the exhaustive pass
+            {
+                float g0 = CUDART_INF_F, g1 = CUDART_INF_F; int s0 = -1, s1 = -1;
+                for (int s = 0; s < nrS; s++) {
+                    const float2 e = __ldg(seS + s * VELO_SECTORS + secq);
+                    const float g = fmaxf(fmaxf(e.x - el, el - e.y), 0.0f);
+                    if (g < g0) { g1 = g0; s1 = s0; g0 = g; s0 = s; } else if (g < g1) { g1 = g; s1 = s; }
+                }
+                Window ws; ws.full = false; ws.wrapped = false; ws.gam = 0.f;
+                ws.b0 = max(bq - 1, 0); ws.b1 = min(bq + 1, VELO_AZ_BINS - 1);
+                if (s0 >= 0) merge_key(scan_ring(sorted, csS + s0 * (VELO_AZ_BINS + 1), s0, ws, mx, my, mz, thr_f), ki, kj);
+                if (s1 >= 0) merge_key(scan_ring(sorted, csS + s1 * (VELO_AZ_BINS + 1), s1, ws, mx, my, mz, thr_f), ki, kj);
+            }
+            // exhaustive pass over all rings, pruned by the current bound on d2_j (velo.h:825-848)
+            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+            Window w = make_window(bound, az, D, rho);
+            for (int s = 0; s < nrS; s++) {
+                if (ring_gap(seS + s * VELO_SECTORS, w, el) > w.gam) continue;
+                const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, w, mx, my, mz, thr_f);
+                if (k == KEY_INF) continue;
+                const u64 oj = kj;
+                merge_key(k, ki, kj);
+                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+            }
+
+            velo_icp_corr rec;
+            rec.src_ring = sm; rec.src_idx = smi; rec.np_s_i = -1; rec.np_i = 0; rec.np_s_j = -1; rec.np_j = 0; rec.np_k = -1; rec.kept = 0;
+            rec.normal[0] = rec.normal[1] = rec.normal[2] = 0.f; rec.v0[0] = rec.v0[1] = rec.v0[2] = 0.f; rec.residual = 0.0;
+            if (ki != KEY_INF) { rec.np_s_i = key_ring(ki); rec.np_i = key_idx(ki); }
+            if (kj != KEY_INF) { rec.np_s_j = key_ring(kj); rec.np_j = key_idx(kj); }
+            if (ki != KEY_INF && kj != KEY_INF) {                        // velo.h:849-851
+                const int si = rec.np_s_i, ni = rec.np_i, sj = rec.np_s_j, nj = rec.np_j;
+                const int ri0 = __ldg(rsS + si), Ln = __ldg(rsS + si + 1) - ri0;
+                const int k1 = (ni + 1) % Ln, k2 = (ni - 1 + Ln) % Ln;  // velo.h:852-863
+                const float4 a1 = __ldg(ptsS + ri0 + k1), a2 = __ldg(ptsS + ri0 + k2);
+                const float n1 = d2f(a1.x, a1.y, a1.z, mx, my, mz), n2 = d2f(a2.x, a2.y, a2.z, mx, my, mz);
+                const int nk = (n1 < n2) ? k1 : k2;
+                rec.np_k = nk;
+                const float4 v0 = __ldg(ptsS + ri0 + ni), v1 = __ldg(ptsS + __ldg(rsS + sj) + nj), v2 = (n1 < n2) ? a1 : a2;
+                // Eigen::Vector3f (v1-v0).cross(v2-v0), norm(), operator/= (velo.h:868-874)
+                const float ax = __fsub_rn(v1.x, v0.x), ay = __fsub_rn(v1.y, v0.y), az3 = __fsub_rn(v1.z, v0.z);
+                const float bx = __fsub_rn(v2.x, v0.x), by = __fsub_rn(v2.y, v0.y), bz = __fsub_rn(v2.z, v0.z);
+                float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az3, by));
+                float ny = __fsub_rn(__fmul_rn(az3, bx), __fmul_rn(ax, bz));
+                float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+                const float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(nx, nx), __fadd_rn(__fmul_rn(ny, ny), __fmul_rn(nz, nz))));
+                rec.v0[0] = v0.x; rec.v0[1] = v0.y; rec.v0[2] = v0.z;
+                if (nn < U.norm_thr_f) { rec.kept = 2; }                 // velo.h:873
+                else {
+                    nx = __fdiv_rn(nx, nn); ny = __fdiv_rn(ny, nn); nz = __fdiv_rn(nz, nn);
+                    rec.normal[0] = nx; rec.normal[1] = ny; rec.normal[2] = nz;
+                    // cost3DPD (costfunctions.h:40-53): M = R p; M += t - o; r = M . n
+                    const double dnx = nx, dny = ny, dnz = nz;
+                    const double m0 = y0 + (P.t[0] - (double)v0.x), m1 = y1 + (P.t[1] - (double)v0.y), m2 = y2 + (P.t[2] - (double)v0.z);
+                    res = m0 * dnx + m1 * dny + m2 * dnz;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const double *d = P.dR + 9 * k;
+                        const double e0 = d[0] * x0 + d[1] * x1 + d[2] * x2, e1 = d[3] * x0 + d[4] * x1 + d[5] * x2, e2 = d[6] * x0 + d[7] * x1 + d[8] * x2;
+                        J[k] = e0 * dnx + e1 * dny + e2 * dnz;
+                    }
+                    J[3] = dnx; J[4] = dny; J[5] = dnz;
+                    // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
+                    const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
+                    rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
+                    rho0h = 0.5 * U.weight * bb * log(sum);
+                    rec.kept = 1; rec.residual = res;
+                    kept = true;
+                }
+            }
+            if (corr) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
+                corr[q] = rec;
+            }
+        }
+        kept_local += kept ? 1 : 0;
+        warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
+    }
+    // reduce
+    for (int o = 16; o > 0; o >>= 1) kept_local += __shfl_down_sync(FULL, kept_local, o);
+    if (lane == 0 && kept_local) atomicAdd(&s_kept, kept_local);
+    double *pout = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64;
+    block_neq_finish(s_red, acc, raw, pout);
+    if (tid == 0) { pout[56] = (double)s_kept; pout[57] = (double)s_kept; pout[58] = (double)(q1 > q0 ? q1 - q0 : 0); }
+}
+
+// fixed-order sum of the per-CTA partials of one unit: out[u][0..58]
+__global__ void k_neq_reduce(const double *__restrict__ partial, double *__restrict__ out, int ctas) {
+    const int u = blockIdx.x, t = threadIdx.x;
+    if (t >= VELO_NEQ_STRIDE) return;
+    double s = 0.0;
+    if (t < 59) for (int c = 0; c < ctas; c++) s += partial[((size_t)u * ctas + c) * 64 + t];
+    out[(size_t)u * VELO_NEQ_STRIDE + t] = s;
+}
+
+void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int ctas,
+                double *partial, double *out, velo_icp_corr *corr) {
+    if (n_units <= 0) return;
+    dim3 g(ctas, n_units);
+    if (L.pre) L.pre(L.user, VK_ICP_PASS);
+    k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, corr);
+    if (L.post) L.post(L.user, VK_ICP_PASS);
+    if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);
+    k_neq_reduce<<<n_units, 64, 0, L.stream>>>(partial, out, ctas);
+    if (L.post) L.post(L.user, VK_NEQ_REDUCE);
+}

@@ -1,0 +1,313 @@
+// velo_kernels.cu — hand-written sm_100a kernels of the VELO front end (SURVEY.md §8 a3–a13).
+//
+// Compiled with -fmad=false; in addition every index-determining float expression uses the explicit
+// round-to-nearest intrinsics (__fadd_rn/__fmul_rn/__fdiv_rn, never contracted) in exactly the operation
+// order of the reference's FMA-free x86-64 build (hazards H2/H3).  Nothing here is GEMM shaped: the work is
+// streaming / gather / neighbour search over SoA-of-float4 buffers, bounded by HBM and L1/L2 behaviour.
+#include "velo_dev.cuh"
+
+#include "velo_common.cuh"
+
+// ------------------------------------------------------------------------------------------------ a3: ingest
+// kitti.h:164-176: flag(i) = i>0 && x_i>0 && (y_i>0)!=(y_{i-1}>0) on the UNtransformed points.
+__global__ void __launch_bounds__(256) k_ingest_flags(DevBuffers B, int slot0) {
+    const int slot = slot0 + blockIdx.y;
+    const int n = B.n_points[slot];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const float4 *raw = B.raw + (size_t)slot * B.N;
+    float x = 0.f, y = 0.f;
+    if (i < n) { float2 xy = *reinterpret_cast<const float2 *>(raw + i); x = xy.x; y = xy.y; }
+    float py = __shfl_up_sync(FULL, y, 1);
+    if (lane == 0 && i > 0 && i < n) py = raw[i - 1].y;
+    bool f = (i > 0) && (i < n) && (x > 0.f) && ((y > 0.f) != (py > 0.f));
+    unsigned m = __ballot_sync(FULL, f);
+    if (lane == 0 && i < n) B.flagbits[(size_t)slot * (B.N / 32) + (i >> 5)] = m;
+}
+
+// ring id = running count of flags; ring_start[ring] = position of the flagged point (kitti.h:169-175)
+__global__ void __launch_bounds__(1024) k_ingest_rings(DevBuffers B, int slot0) {
+    __shared__ int s_w[33];
+    const int slot = slot0 + blockIdx.x, tid = threadIdx.x;
+    const int n = B.n_points[slot];
+    const int W = (n + 31) >> 5, wpt = (W + blockDim.x - 1) / blockDim.x;
+    const uint32_t *bits = B.flagbits + (size_t)slot * (B.N / 32);
+    int *rs = B.ring_start + (size_t)slot * (B.R + 1);
+    int w0 = min(W, tid * wpt), w1 = min(W, w0 + wpt), cnt = 0;
+    for (int w = w0; w < w1; w++) cnt += __popc(bits[w]);
+    int total;
+    int run = block_excl_scan(cnt, s_w, total);
+    for (int w = w0; w < w1; w++) {
+        uint32_t b = bits[w];
+        while (b) {
+            int bit = __ffs(b) - 1; b &= b - 1;
+            ++run;
+            if (run <= B.R) rs[run] = w * 32 + bit;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nr = n > 0 ? total + 1 : 0;
+        int st = 0;
+        if (nr > B.R) { st = VELO_ERR_CAPACITY; nr = 0; }   // hazard H12: ring count is data dependent
+        rs[0] = 0;
+        if (nr > 0) rs[nr] = n;
+        B.n_rings[slot] = nr;
+        B.status[slot] = st;
+    }
+}
+
+// velo_to_cam transform (kitti.h:162, PCL dense branch: left-to-right f32) + reverse/half-rotate reorder (kitti.h:178-183)
+__global__ void __launch_bounds__(256) k_ingest_permute(DevBuffers B, DevCalib cal, int slot0) {
+    __shared__ int s_rs[VELO_MAX_RINGS_HARD + 1];
+    const int slot = slot0 + blockIdx.y;
+    const int n = B.n_points[slot], nr = B.n_rings[slot];
+    if ((int)(blockIdx.x * blockDim.x) >= n || nr == 0) return;
+    const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
+    for (int i = threadIdx.x; i <= nr; i += blockDim.x) s_rs[i] = rs[i];
+    __syncthreads();
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    int lo = 0, hi = nr - 1;               // largest r with s_rs[r] <= d
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_rs[mid] <= d) lo = mid; else hi = mid - 1; }
+    const int r0 = s_rs[lo], L = s_rs[lo + 1] - r0, i = d - r0;
+    const int src = r0 + (L - 1 - (i + L / 2) % L);
+    const float4 p = __ldg(B.raw + (size_t)slot * B.N + src);
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cal.vtc[0], p.x), __fmul_rn(cal.vtc[1], p.y)), __fmul_rn(cal.vtc[2], p.z)), cal.vtc[3]);
+    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cal.vtc[4], p.x), __fmul_rn(cal.vtc[5], p.y)), __fmul_rn(cal.vtc[6], p.z)), cal.vtc[7]);
+    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cal.vtc[8], p.x), __fmul_rn(cal.vtc[9], p.y)), __fmul_rn(cal.vtc[10], p.z)), cal.vtc[11]);
+    o.w = 1.0f;
+    B.pts[(size_t)slot * B.N + d] = o;
+}
+
+// ------------------------------------------------------------------------------------------------ a4: neighbour index
+// Index frame = velodyne-like frame (rotation part of velo_to_cam transposed): rings are cones about its z axis,
+// so a ring has a narrow elevation interval and is nearly sorted in azimuth.  Used ONLY for pruning; all
+// distances / decisions are evaluated on the cam-0 coordinates exactly as the reference does.
+// one CTA per (ring, slot): counting sort of the ring by azimuth bin + per-sector elevation intervals.
+// Replaces the 64 KdTreeFLANN::setInputCloud calls of lru.h:17-20.
+__global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal, int slot0) {
+    __shared__ int s_hist[VELO_AZ_BINS];
+    __shared__ int s_cur[VELO_AZ_BINS];
+    __shared__ int s_lo[VELO_SECTORS], s_hi[VELO_SECTORS];
+    __shared__ int s_w[33];
+    const int slot = slot0 + blockIdx.y, ring = blockIdx.x, tid = threadIdx.x;
+    if (ring >= B.n_rings[slot]) return;
+    const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
+    const int r0 = rs[ring], L = rs[ring + 1] - r0;
+    const float4 *pts = B.pts + (size_t)slot * B.N + r0;
+    for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) { s_hist[i] = 0; s_cur[i] = 0; }
+    if (tid < VELO_SECTORS) { s_lo[tid] = f2ord(CUDART_INF_F); s_hi[tid] = f2ord(-CUDART_INF_F); }
+    __syncthreads();
+    for (int i = tid; i < L; i += blockDim.x) {
+        float4 p = pts[i];
+        float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
+        int b = az_bin(atan2f(vy, vx));
+        int e = f2ord(atan2f(vz, sqrtf(vx * vx + vy * vy)));
+        atomicAdd(&s_hist[b], 1);
+        atomicMin(&s_lo[b / VELO_BINS_PER_SECTOR], e);
+        atomicMax(&s_hi[b / VELO_BINS_PER_SECTOR], e);
+    }
+    __syncthreads();
+    // exclusive scan of 512 bins with 256 threads (2 bins each)
+    int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1], total;
+    int ex = block_excl_scan(a0 + a1, s_w, total);
+    s_hist[2 * tid] = ex; s_hist[2 * tid + 1] = ex + a0;
+    __syncthreads();
+    int *cs = B.cell_start + ((size_t)slot * B.R + ring) * (VELO_AZ_BINS + 1);
+    for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) cs[i] = r0 + s_hist[i];
+    if (tid == 0) cs[VELO_AZ_BINS] = r0 + L;
+    if (tid < VELO_SECTORS)
+        B.sec_elev[((size_t)slot * B.R + ring) * VELO_SECTORS + tid] = make_float2(ord2f(s_lo[tid]), ord2f(s_hi[tid]));
+    float4 *sorted = B.sorted + (size_t)slot * B.N + r0;
+    for (int i = tid; i < L; i += blockDim.x) {
+        float4 p = pts[i];
+        float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
+        int b = az_bin(atan2f(vy, vx));
+        int pos = s_hist[b] + atomicAdd(&s_cur[b], 1);
+        p.w = __int_as_float(i);
+        sorted[pos] = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ a5: projection
+// One warp per (ring, slot), all cameras.  Lanes project + FOV-test 32 points at a time; lane `cam` then runs
+// the reference's sequential occlusion stack (velo.h:351-368) over the survivors of its camera.  The stack IS
+// the output array, so a pop only re-reads the new top (hazards H6/H7).
+#define PROJ_WARPS 4
+__global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DevBuffers B, DevCalib cal, int slot0) {
+    __shared__ float4 s_p[PROJ_WARPS][32];
+    __shared__ float s_c[PROJ_WARPS][VELO_MAX_CAMS][3][32];
+    const int slot = slot0 + blockIdx.y, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ring = blockIdx.x * PROJ_WARPS + wid;
+    if (ring >= B.n_rings[slot]) return;
+    const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
+    const int r0 = rs[ring], L = rs[ring + 1] - r0;
+    const float4 *pts = B.pts + (size_t)slot * B.N + r0;
+    const int C = cal.num_cams;
+    // per-camera stack state lives in lane == cam
+    int depth = 0; float top_x = 0.f, top_z = 0.f;
+    float2 *proj = nullptr; float4 *valid = nullptr; float tz = 0.f;
+    if (lane < C) {
+        proj = B.proj + ((size_t)slot * B.C + lane) * B.N + r0;
+        valid = B.valid + ((size_t)slot * B.C + lane) * B.N + r0;
+        tz = cal.cam_t[lane][2];
+    }
+    for (int c0 = 0; c0 < L; c0 += 32) {
+        const int i = c0 + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < L) p = pts[i];
+        s_p[wid][lane] = p;
+        unsigned mymask = 0;
+        for (int cam = 0; cam < C; cam++) {
+            float ppx = __fadd_rn(p.x, cal.cam_t[cam][0]), ppy = __fadd_rn(p.y, cal.cam_t[cam][1]), ppz = __fadd_rn(p.z, cal.cam_t[cam][2]); // velo.h:346
+            float cx = __fdiv_rn(ppx, ppz), cy = __fdiv_rn(ppy, ppz);                                                             // velo.h:347
+            bool in = (i < L) && (ppz > 0.f) && (cx >= cal.fov[cam][0]) && (cx < cal.fov[cam][1]) && (cy >= cal.fov[cam][2]) && (cy < cal.fov[cam][3]);
+            unsigned m = __ballot_sync(FULL, in);
+            s_c[wid][cam][0][lane] = cx; s_c[wid][cam][1][lane] = cy; s_c[wid][cam][2][lane] = ppz;
+            if (lane == cam) mymask = m;
+        }
+        __syncwarp();
+        if (lane < C) {
+            while (mymask) {
+                const int b = __ffs(mymask) - 1; mymask &= mymask - 1;
+                const float cx = s_c[wid][lane][0][b], ppz = s_c[wid][lane][2][b];
+                while (depth > 0 && cx < top_x && ppz < top_z) {         // velo.h:351-358: pop occluded
+                    depth--;
+                    if (depth > 0) { top_x = proj[depth - 1].x; top_z = __fadd_rn(valid[depth - 1].z, tz); }
+                }
+                if (depth > 0 && cx < top_x && ppz > top_z) continue;      // velo.h:360-365: skip occluded
+                proj[depth] = make_float2(cx, s_c[wid][lane][1][b]);        // velo.h:366-368
+                float4 q = s_p[wid][b]; q.w = 1.0f;
+                valid[depth] = q;
+                depth++; top_x = cx; top_z = ppz;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < C) B.proj_count[((size_t)slot * B.C + lane) * B.R + ring] = depth;
+}
+
+// ------------------------------------------------------------------------------------------------ a6/a7: depth association
+__device__ __forceinline__ float lerp1(float p1, float p2, float start, float end, float mid) {   // utility.h:20-29
+    float a = __fdiv_rn(__fsub_rn(mid, start), __fsub_rn(end, start));
+    float b = __fsub_rn(1.0f, a);
+    return __fadd_rn(__fmul_rn(p1, b), __fmul_rn(p2, a));
+}
+__device__ __forceinline__ float3 lerp3(float4 p1, float4 p2, float start, float end, float mid) { // utility.h:7-19
+    float a = __fdiv_rn(__fsub_rn(mid, start), __fsub_rn(end, start));
+    float b = __fsub_rn(1.0f, a);
+    return make_float3(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p2.x, a)), __fadd_rn(__fmul_rn(p1.y, b), __fmul_rn(p2.y, a)),
+                       __fadd_rn(__fmul_rn(p1.z, b), __fmul_rn(p2.z, a)));
+}
+__device__ __forceinline__ bool width_ok(float dx, const DevCalib &cal) {   // hazard H1 (velo.h:416,419)
+    if (cal.abs_truncates) return abs((int)dx) == 0;                        // (double)abs((int)dx) < 0.015  <=>  (int)dx == 0
+    return fabsf(dx) < cal.assoc_thr;
+}
+
+// one thread per keypoint: the ring loop, binary search and bilinear patch of velo.h:390-492, step for step (H4/H5).
+// grid = (keypoint chunks, cameras, slots*sets)
+__global__ void __launch_bounds__(128) k_assoc_search(DevBuffers B, DevCalib cal, int slot0, int set0, int nsets, int cam0) {
+    __shared__ int s_rs[VELO_MAX_RINGS_HARD + 1];
+    __shared__ int s_cnt[VELO_MAX_RINGS_HARD];
+    const int cam = cam0 + blockIdx.y;
+    const int slot = slot0 + blockIdx.z / nsets, set = set0 + blockIdx.z % nsets;
+    const int nr = B.n_rings[slot];
+    const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + set) * B.C + cam;
+    const int F = B.n_kp[sc];
+    if ((int)(blockIdx.x * blockDim.x) >= F) return;
+    const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
+    const int *pc = B.proj_count + ((size_t)slot * B.C + cam) * B.R;
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) { s_rs[i] = rs[i]; s_cnt[i] = pc[i]; }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    const float2 *proj = B.proj + ((size_t)slot * B.C + cam) * B.N;
+    const float4 *valid = B.valid + ((size_t)slot * B.C + cam) * B.N;
+    const float2 kp = B.kp[sc * B.F + k];
+    int last = -1, hit = 0;
+    float4 out = make_float4(0.f, 0.f, 0.f, 1.0f);
+    for (int s = 0; s < nr; s++) {
+        const int cnt = s_cnt[s];
+        if (cnt <= 1) { last = -1; continue; }                       // velo.h:400-403
+        const float2 *ps = proj + s_rs[s];
+        int lo = 0, hi = cnt - 2, mid = 0;
+        bool found = false;
+        while (lo <= hi) {                                           // velo.h:404-412
+            mid = (lo + hi) >> 1;
+            const float2 a = ps[mid];
+            if (a.x > kp.x) { hi = mid - 1; continue; }
+            const float2 b = ps[mid + 1];
+            if (b.x <= kp.x) { lo = mid + 1; continue; }
+            found = true;
+            if (last != -1) {
+                const float2 *pq = proj + s_rs[s - 1];
+                const float2 c = pq[last], d = pq[last + 1];
+                if (((a.y > kp.y) != (c.y > kp.y)) && width_ok(__fsub_rn(a.x, b.x), cal) && width_ok(__fsub_rn(c.x, d.x), cal)) {
+                    const float4 *vs = valid + s_rs[s], *vq = valid + s_rs[s - 1];
+                    float3 i1 = lerp3(vs[mid], vs[mid + 1], a.x, b.x, kp.x);          // velo.h:445-450
+                    float3 i2 = lerp3(vq[last], vq[last + 1], c.x, d.x, kp.x);        // velo.h:451-456
+                    float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                       // velo.h:457-462
+                    float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                       // velo.h:463-468
+                    float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
+                    out = make_float4(r.x, r.y, r.z, 1.0f);
+                    hit = 1;
+                }
+            }
+            last = mid;                                              // velo.h:483
+            break;
+        }
+        if (!found) last = -1;                                       // velo.h:487-489
+        if (hit) break;                                              // velo.h:490
+    }
+    B.hit_tmp[sc * B.F + k] = hit;
+    if (hit) B.kpwd_tmp[sc * B.F + k] = out;
+}
+
+// stable compaction in keypoint order (hazard H13): has_depth[k] = running hit count, kpwd appended (velo.h:479-481)
+__global__ void __launch_bounds__(256) k_assoc_compact(DevBuffers B, int slot0, int set0, int nsets, int cam0) {
+    __shared__ int s_w[33];
+    const int cam = cam0 + blockIdx.x;
+    const int slot = slot0 + blockIdx.y / nsets, set = set0 + blockIdx.y % nsets;
+    const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + set) * B.C + cam;
+    const int F = B.n_kp[sc];
+    const int *hit = B.hit_tmp + sc * B.F;
+    int base = 0;
+    for (int k0 = 0; k0 < F; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        int h = (k < F) ? hit[k] : 0, total;
+        int ex = block_excl_scan(h, s_w, total);
+        if (k < F) {
+            B.has_depth[sc * B.F + k] = h ? base + ex : -1;
+            if (h) B.kpwd[sc * B.F + base + ex] = B.kpwd_tmp[sc * B.F + k];
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) B.n_hits[sc] = base;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+#define PRE(k) do { if (L.pre) L.pre(L.user, (k)); } while (0)
+#define POST(k) do { if (L.post) L.post(L.user, (k)); } while (0)
+
+void launch_ingest(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count) {
+    dim3 g((B.N + 255) / 256, count);
+    PRE(VK_INGEST_FLAGS); k_ingest_flags<<<g, 256, 0, L.stream>>>(B, slot0); POST(VK_INGEST_FLAGS);
+    PRE(VK_INGEST_RINGS); k_ingest_rings<<<count, 1024, 0, L.stream>>>(B, slot0); POST(VK_INGEST_RINGS);
+    PRE(VK_INGEST_PERMUTE); k_ingest_permute<<<g, 256, 0, L.stream>>>(B, cal, slot0); POST(VK_INGEST_PERMUTE);
+}
+void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count) {
+    dim3 g(B.R, count);
+    PRE(VK_INDEX_BUILD); k_index_build<<<g, 256, 0, L.stream>>>(B, cal, slot0); POST(VK_INDEX_BUILD);
+}
+void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count) {
+    dim3 g((B.R + PROJ_WARPS - 1) / PROJ_WARPS, count);
+    PRE(VK_PROJECT); k_project<<<g, PROJ_WARPS * 32, 0, L.stream>>>(B, cal, slot0); POST(VK_PROJECT);
+}
+void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams) {
+    dim3 g((B.F + 127) / 128, ncams, count * nsets);
+    PRE(VK_ASSOC_SEARCH); k_assoc_search<<<g, 128, 0, L.stream>>>(B, cal, slot0, set0, nsets, cam0); POST(VK_ASSOC_SEARCH);
+    dim3 g2(ncams, count * nsets);
+    PRE(VK_ASSOC_COMPACT); k_assoc_compact<<<g2, 256, 0, L.stream>>>(B, slot0, set0, nsets, cam0); POST(VK_ASSOC_COMPACT);
+}

@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""bench.py — frames/s of the VELO per-frame front end (scan ingest + stereo depth association + ICP correspondence
++ J^T J) on synthetic KITTI-shaped data, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames T] [--impl ours|reference]
+
+A step = one pass of the whole front end over a batch of T consecutive frames per GPU (T frame pairs + 1 halo scan):
+ingest/segment T+1 scans, build T+1 neighbour indices, project + associate (2 cameras x 2 keypoint sets) T frames,
+f2f_iterations x icp_iterations = 6 ICP passes (icp_skip = 1, ~120k queries vs ~120k targets) and 2 visual residual
+assemblies per frame pair, each reduced to 6x6 normal equations.  `value` times that with inputs resident in HBM;
+`e2e` times upload (pinned host -> device) + the same work + download of the results, through the C ABI.
+`--impl reference` times the CPU restatement of the reference path (oracle/, kd-tree per ring like PCL) on all host
+cores with the reference's own call pattern.  See DESIGN.md "Measurement".
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s (scan+stereo assoc+ICP corr+J^TJ)"
+
+
+def load_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (pynvml; falls back to nothing if unavailable)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_bytes(abi, prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_vis, kept):
+    """Compulsory traffic per kernel class for one step (DESIGN.md 'Algorithmic bytes'): every input read once,
+    every required output written once.  npnt/nr/ptot over the T+1 slots; frame pairs are slots 1..T."""
+    C, R = prm.num_cams, 0
+    AZ, SEC = 512, 64
+    n_all = float(npnt.sum()); rings_all = float(nr.sum())
+    n_fr = float(npnt[1:].sum()); rings_fr = float(nr[1:].sum())
+    b = {}
+    b["ingest_flags"] = 16 * n_all + n_all / 8
+    b["ingest_rings"] = n_all / 8 + 4 * (rings_all + len(nr))
+    b["ingest_permute"] = 16 * n_all + 16 * n_all
+    b["index_build"] = 16 * n_all + 16 * n_all + rings_all * (4 * (AZ + 1) + 8 * SEC)
+    b["project_occlude"] = 16 * n_fr + float(ptot[1:].sum()) * 24 + 4 * C * rings_fr
+    hits = float(nhits[1:].sum()); F = float(nkp[1:].sum())
+    b["assoc_search"] = 2 * (float(ptot[1:].sum()) * 8) + F * 8 + F * 4 + hits * (4 * 16 + 16)   # proj x read (per set), kp, flags, 4 bracketing points + result
+    b["assoc_compact"] = F * 4 + F * 4 + hits * 32
+    Q = n_fr                                                                                     # icp_skip = 1
+    tgt = float(npnt[:-1].sum()); rings_t = float(nr[:-1].sum())
+    b["icp_pass"] = n_passes * (16 * Q / max(prm.icp_skip, 1) + 16 * tgt + rings_t * (4 * (AZ + 1) + 8 * SEC)) + 48 * float(kept) + 512 * n_passes * (len(npnt) - 1)
+    b["visual_residuals"] = n_vis * (float(nmatch[1:].sum()) * (8 + 2 * 4 + 2 * 16 + 2 * 8)) + 512 * n_vis * (len(npnt) - 1)
+    b["neq_reduce"] = 0.0
+    return b
+
+
+def run_ours(args, rank, world, local_rank):
+    velo = importlib.import_module("vision-enhanced-lidar-odometry_b200")
+    api, synth, abi = velo.api, velo.synth, velo.abi
+    import numpy as np
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    T = args.frames
+    P, Tr, w, h = synth.calib_raw(args.rig)
+    cal = api.calib_from_kitti(P, Tr, w, h)
+    prm = api.default_params(max_slots=T + 1, max_points=131072, max_rings=96, max_features=args.features, max_matches=args.features,
+                             icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
+    ctx = api.Context(prm, cal, device=local_rank)
+    pool = api.PinnedPool()
+    frame0 = 1000 + rank * T          # frame-sharded: rank g owns frames [frame0, frame0 + T) plus the halo frame0 - 1
+    t_gen = time.time()
+    batch = synth.Batch(frame0 - 1, T + 1, prm, rig=args.rig, alloc=pool.zeros)
+    t_gen = time.time() - t_gen
+    icp = pool.zeros((T + 1, batch.n_passes, abi.NEQ_STRIDE), np.float64)
+    vis = pool.zeros((T + 1, batch.n_vis, abi.NEQ_STRIDE), np.float64)
+    hd = pool.zeros((T + 1, 2, prm.num_cams, prm.max_features), np.int32)
+    nh = pool.zeros((T + 1, 2, prm.num_cams), np.int32)
+    h2d = sum(a.nbytes for a in (batch.scans, batch.n_points, batch.kp, batch.n_kp, batch.matches, batch.n_matches)) \
+        + (T + 1) * batch.n_passes * 400 + (T + 1) * batch.n_vis * 72
+    d2h = icp.nbytes + vis.nbytes + hd.nbytes + nh.nbytes
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx.batch_upload(0, batch)
+    ctx.profile(True)
+    # ---------------- device-resident timing (`value`)
+    for _ in range(args.warmup):
+        ctx.batch_run(0, T + 1)
+    barrier()
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    clocks = ClockSampler(local_rank); clocks.start()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        ctx.batch_run(0, T + 1)
+    ms = ctx.timer_end()
+    barrier()
+    clk = clocks.stop()
+    launches = ctx.launch_count() - l0
+    prof = ctx.profile_read()
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = world * T / (ms_per_step * 1e-3)
+    # ---------------- end-to-end timing through the C ABI with host buffers (`e2e`)
+    for _ in range(2):
+        ctx.batch_upload(0, batch); ctx.batch_run(0, T + 1); ctx.batch_download(0, T + 1, icp, vis, hd, nh)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        ctx.batch_upload(0, batch)
+        ctx.batch_run(0, T + 1)
+        ctx.batch_download(0, T + 1, icp, vis, hd, nh)
+        if dist is not None:   # host gather of the per-frame normal equations (the only cross-GPU traffic)
+            import torch
+            g = [torch.empty_like(torch.from_numpy(icp)) for _ in range(world)] if rank == 0 else None
+            dist.gather(torch.from_numpy(icp).cuda(), [x.cuda() for x in g] if g else None, dst=0)
+    e2e_ms = ctx.timer_end()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall)) / args.steps
+    e2e_value = world * T / (e2e_ms * 1e-3)
+
+    # ---------------- roofline of the dominant kernel + per-kernel table
+    npnt, nr, ptot, st = ctx.batch_counts(0, T + 1)
+    assert (st == 0).all(), "a scan exceeded max_rings"
+    kept = icp[1:, :, 56].sum()
+    ab = algorithmic_bytes(abi, prm, npnt, nr, ptot, nh, batch.n_kp, batch.n_matches, batch.n_passes, batch.n_vis, kept)
+    peak, peak_src = load_peak()
+    kernels = {}
+    for name, (kms, n) in prof.items():
+        per_launch_ms = kms / n
+        bytes_per_launch = ab.get(name, 0.0)
+        kernels[name] = {"ms_per_launch": round(per_launch_ms, 4), "launches": n, "share": round(kms / ms, 4),
+                         "alg_MB_per_launch": round(bytes_per_launch / 1e6, 2),
+                         "GBps": round(bytes_per_launch / 1e9 / (per_launch_ms * 1e-3), 1) if per_launch_ms > 0 else None}
+    dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+            if tj.get("kernel") == dom and tj.get("frames") == T:
+                traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    ach = kernels[dom]["GBps"]
+    roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+            "traffic": traffic, "peak_source": peak_src,
+            "note": "icp_pass is compute/latency bound (exhaustive exact neighbour search), see DESIGN.md"}
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 geometry/indices, f64 residuals+JtJ", "data": "synthetic",
+        "config": {"workload": f"{T}-frame synthetic KITTI sequence per GPU (BASELINE configs[1]+[2]): ingest+index {T + 1} scans, "
+                               f"project+associate {prm.num_cams} cams x 2 keypoint sets x {args.features} features, "
+                               f"{batch.n_passes} ICP passes/frame (icp_skip={prm.icp_skip}, ~{int(npnt.mean())} pts vs ~{int(npnt.mean())} pts) + "
+                               f"{batch.n_vis} visual assemblies/frame, 6x6 normal equations",
+                   "frames_per_gpu": T, "points_per_scan": int(npnt.mean()), "rings": int(nr.mean()), "cams": prm.num_cams,
+                   "features_per_image": args.features, "icp_passes": batch.n_passes, "icp_skip": prm.icp_skip,
+                   "in_fov_per_cam": int(ptot[1:].mean()), "sharding": f"frames over {world} GPU(s), no collective on the data path",
+                   "l2": f"inputs {batch.scans.nbytes / 1e9:.2f} GB/step >> 126 MB L2 (no flush needed)"},
+        "clocks": clk,
+        "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": round(e2e_ms, 3)},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "kernels": kernels,
+        "gen_seconds": round(t_gen, 2),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, prm, cal, synth)
+    ctx.close()
+    pool.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def cpu_baseline(args, prm, cal, synth, frames=None, threads=None):
+    """The oracle restatement (oracle/, kd-tree per ring like PCL's KdTreeFLANN) timed on the host cores: a bounded
+    sample of the same workload — `threads` frame pairs (one per worker) with the full per-frame schedule."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    orc = pyoracle.Oracle()
+    threads = threads or (os.cpu_count() or 1)
+    frames = frames or threads
+    b = synth.Batch(999, frames + 1, prm, rig=args.rig)
+    sec, _, _ = orc.bench_frames(b, prm, cal, threads)
+    return {"value": round(frames / sec, 4), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{frames} frame pairs (one per host thread), same per-frame schedule as the GPU step, {sec:.1f} s wall",
+            "seconds": round(sec, 2)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU algorithm (oracle port: the reference itself cannot be built) on all
+    host threads; a step = `cores` frame pairs of the same workload."""
+    if rank != 0:
+        return
+    velo = importlib.import_module("vision-enhanced-lidar-odometry_b200")
+    api, synth = velo.api, velo.synth
+    P, Tr, w, h = synth.calib_raw(args.rig)
+    cal = api.calib_from_kitti(P, Tr, w, h)
+    prm = api.default_params(max_slots=2, max_points=131072, max_rings=96, max_features=args.features, max_matches=args.features,
+                             icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(args, prm, cal, synth, frames=cores, threads=cores)
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    sec = sum(times) / len(times)
+    val = cores / sec
+    out = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32 geometry/indices, f64 residuals+JtJ", "data": "synthetic",
+           "config": {"workload": "same per-frame schedule as the CUDA arm (ingest + 64 kd-trees, project+associate twice per camera, "
+                                  "6 ICP passes with icp_skip=%d, 2 visual assemblies); a step = %d frame pairs, one per host thread" % (args.icp_skip, cores),
+                      "features_per_image": args.features, "icp_skip": args.icp_skip},
+           "cpu_baseline": {"value": round(val, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+                            "sample": f"{cores} frame pairs per step x {args.steps} steps"},
+           "e2e": {"value": round(val, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=1000, help="frame pairs per GPU per step")
+    ap.add_argument("--features", type=int, default=2000)
+    ap.add_argument("--icp-skip", type=int, default=1)
+    ap.add_argument("--rig", type=int, default=0, help="0 = KITTI stereo, 1 = off-road 4-camera rig")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

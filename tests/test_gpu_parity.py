@@ -1,0 +1,344 @@
+"""-m gpu: every CUDA stage, called through the C ABI (libvelo_gpu.so), against the CPU oracle on identical inputs.
+Bars (BASELINE.json north_star): indices / integer outputs bit-exact; f32 geometry bit-exact (same IEEE ops in the
+same order); f64 residuals within 1e-5 relative; normal equations within 1e-4 relative."""
+import numpy as np
+import pytest
+from conftest import small_scan
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RES = 1e-5      # fp32/fp64 residual tolerance stated by north_star
+RTOL_NEQ = 1e-4      # J^T J tolerance stated by north_star
+
+
+@pytest.fixture(scope="module")
+def ctx(velo, calib):
+    prm = velo.api.default_params(max_slots=4, max_features=8192, max_matches=8192, num_cams=2)
+    c = velo.api.Context(prm, calib)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx4(velo, oracle):
+    """off-road rig: 4 cameras (BASELINE configs[3])"""
+    P, Tr, w, h = velo.synth.calib_raw(1)
+    cal = oracle.calib_from_kitti(P, Tr, w, h)
+    prm = velo.api.default_params(max_slots=2, max_features=8192, max_matches=8192, num_cams=4)
+    c = velo.api.Context(prm, cal)
+    yield c
+    c.close()
+
+
+def test_calibration_matches_oracle(velo, oracle):
+    for rig in (0, 1):
+        P, Tr, w, h = velo.synth.calib_raw(rig)
+        a = velo.api.calib_from_kitti(P, Tr, w, h)
+        b = oracle.calib_from_kitti(P, Tr, w, h)
+        assert bytes(a) == bytes(b)
+
+
+@pytest.mark.parametrize("frame", [7, 123])
+def test_ingest_bit_exact(velo, oracle, calib, ctx, frame):
+    raw, n = velo.synth.scan(frame)
+    ctx.scan_upload(0, raw)
+    pts, rs = ctx.scan_download(0)
+    opts, ors, onr = oracle.segment(raw, calib)
+    assert ctx.scan_info(0) == (n, onr)
+    assert np.array_equal(rs, ors)
+    assert pts.tobytes() == opts.tobytes()
+
+
+def test_ingest_ragged_and_empty(velo, oracle, calib, ctx):
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 31, 32, 33, 1000):
+        raw = (rng.normal(size=(n, 4)) * 10).astype(np.float32)
+        ctx.scan_upload(1, raw)
+        opts, ors, onr = oracle.segment(raw, calib)
+        if onr > ctx.prm.max_rings:          # random points cross the seam constantly: legitimately over capacity
+            with pytest.raises(velo.api.VeloError):
+                ctx.scan_download(1)
+            continue
+        pts, rs = ctx.scan_download(1)
+        assert np.array_equal(rs, ors), n
+        assert pts.tobytes() == opts.tobytes(), n
+
+
+def test_ingest_too_many_rings_is_an_error(velo, ctx):
+    n = 4000
+    raw = np.zeros((n, 4), np.float32)
+    raw[:, 0] = 5.0
+    raw[:, 1] = np.where(np.arange(n) % 2 == 0, 1.0, -1.0)     # every point crosses the seam -> n rings
+    ctx.scan_upload(1, raw)
+    with pytest.raises(velo.api.VeloError) as e:
+        ctx.scan_info(1)
+    assert e.value.code == 4
+
+
+@pytest.mark.parametrize("cam", [0, 1])
+def test_project_bit_exact(velo, oracle, calib, ctx, cam):
+    raw, n = velo.synth.scan(7)
+    ctx.scan_upload(0, raw)
+    ctx.project(0, cam)
+    rc, proj, valid = ctx.project_download(0, cam)
+    opts, ors, _ = oracle.segment(raw, calib)
+    orc, oproj, ovalid = oracle.project(opts, ors, calib, cam)
+    assert np.array_equal(rc, orc)
+    assert proj.tobytes() == oproj.tobytes()
+    assert valid.tobytes() == ovalid.tobytes()
+    assert rc.sum() > 10000
+
+
+def test_project_occlusion_stress(velo, oracle, calib, ctx):
+    """noisy depth so that pops / skips / re-pushes happen constantly (velo.h:351-365)"""
+    raw, n = velo.synth.scan(9)
+    rng = np.random.default_rng(3)
+    raw = raw.copy()
+    raw[:, :3] *= (1.0 + rng.normal(size=(n, 1)).astype(np.float32) * 0.05)
+    ctx.scan_upload(0, raw)
+    opts, ors, _ = oracle.segment(raw, calib)
+    for cam in (0, 1):
+        ctx.project(0, cam)
+        rc, proj, valid = ctx.project_download(0, cam)
+        orc, oproj, ovalid = oracle.project(opts, ors, calib, cam)
+        assert np.array_equal(rc, orc)
+        assert proj.tobytes() == oproj.tobytes() and valid.tobytes() == ovalid.tobytes()
+
+
+@pytest.mark.parametrize("F", [0, 1, 2000, 8000])
+def test_depth_assoc_bit_exact(velo, oracle, calib, ctx, F):
+    raw, n = velo.synth.scan(7)
+    ctx.scan_upload(0, raw)
+    opts, ors, _ = oracle.segment(raw, calib)
+    kpA, kpB, _ = velo.synth.features(7, max(F, 1))
+    for cam in (0, 1):
+        ctx.project(0, cam)
+        orc, oproj, ovalid = oracle.project(opts, ors, calib, cam)
+        for s, kp in enumerate((kpA[cam][:F], kpB[cam][:F])):
+            hd, kpwd = ctx.depth_assoc(0, cam, kp, s)
+            ohd, okpwd = oracle.depth_assoc(ovalid, oproj, orc, kp)
+            assert np.array_equal(hd, ohd)
+            assert kpwd.tobytes() == okpwd.tobytes()
+
+
+def test_depth_assoc_abs_truncates_variant(velo, oracle, calib):
+    """hazard H1: the alternative binding of abs() (int abs(int)) is a runtime switch on both sides"""
+    prm = velo.api.default_params(max_slots=1, abs_truncates=1)
+    c = velo.api.Context(prm, calib)
+    try:
+        raw, n = velo.synth.scan(7)
+        c.scan_upload(0, raw)
+        c.project(0, 0)
+        opts, ors, _ = oracle.segment(raw, calib)
+        orc, oproj, ovalid = oracle.project(opts, ors, calib, 0)
+        kp = velo.synth.features(7, 2000)[0][0]
+        hd, kpwd = c.depth_assoc(0, 0, kp, 0)
+        ohd, okpwd = oracle.depth_assoc(ovalid, oproj, orc, kp, abs_truncates=1)
+        assert np.array_equal(hd, ohd) and kpwd.tobytes() == okpwd.tobytes()
+        ohd0, _ = oracle.depth_assoc(ovalid, oproj, orc, kp, abs_truncates=0)
+        assert (ohd >= 0).sum() >= (ohd0 >= 0).sum()
+    finally:
+        c.close()
+
+
+def _check_icp(velo, oracle, params, ctx, ptsM, rsM, ptsS, rsS, pose, it, skip, mode):
+    corr, neq, kept = ctx.icp_pass(1, 0, pose, it, skip)
+    ocorr, oneq, okept = oracle.icp_pass(ptsM, rsM, ptsS, rsS, pose, it, skip, params, mode)
+    assert len(corr) == len(ocorr)
+    for f in ("src_ring", "src_idx", "kept", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
+        bad = np.nonzero(corr[f] != ocorr[f])[0]
+        assert len(bad) == 0, (f, len(bad), corr[bad[:3]], ocorr[bad[:3]])
+    assert kept == okept
+    k = ocorr["kept"] == 1
+    assert corr["normal"][k].tobytes() == ocorr["normal"][k].tobytes()
+    assert corr["v0"][k].tobytes() == ocorr["v0"][k].tobytes()
+    np.testing.assert_allclose(corr["residual"][k], ocorr["residual"][k], rtol=RTOL_RES, atol=1e-9)
+    np.testing.assert_allclose(corr["jacobian"][k], ocorr["jacobian"][k], rtol=RTOL_RES, atol=1e-9)
+    scale = np.abs(oneq[:56]).max()
+    np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * max(scale, 1e-30))
+    assert neq[56] == oneq[56] and neq[58] == oneq[58]
+    return kept
+
+
+@pytest.mark.parametrize("it,skip", [(1, 1), (2, 1), (1, 5), (1, 200)])
+def test_icp_small_vs_bruteforce_truth(velo, oracle, calib, params, ctx, it, skip):
+    """thinned scans: the oracle's brute-force NN (truth; ties -> lower index) defines the indices"""
+    rawM, rawS = small_scan(velo, 8), small_scan(velo, 7)
+    ctx.scan_upload(1, rawM); ctx.scan_upload(0, rawS)
+    ptsM, rsM, _ = oracle.segment(rawM, calib)
+    ptsS, rsS, _ = oracle.segment(rawS, calib)
+    pose = velo.synth.pose_guess(8, 0)
+    kept = _check_icp(velo, oracle, params, ctx, ptsM, rsM, ptsS, rsS, pose, it, skip, 0)
+    if skip == 1:
+        assert kept > 100
+
+
+@pytest.mark.parametrize("it,pass_idx", [(1, 0), (2, 3)])
+def test_icp_full_scan_indices_exact(velo, oracle, calib, params, ctx, it, pass_idx):
+    """BASELINE configs[2]: 120k vs 120k, icp_skip = 1.  Oracle in kd-tree mode (itself checked against brute force)."""
+    rawM, nM = velo.synth.scan(8)
+    rawS, nS = velo.synth.scan(7)
+    ctx.scan_upload(1, rawM); ctx.scan_upload(0, rawS)
+    ptsM, rsM, _ = oracle.segment(rawM, calib)
+    ptsS, rsS, _ = oracle.segment(rawS, calib)
+    pose = velo.synth.pose_guess(8, pass_idx)
+    kept = _check_icp(velo, oracle, params, ctx, ptsM, rsM, ptsS, rsS, pose, it, 1, 1)
+    assert kept > (50000 if it == 1 else 5000)
+
+
+def test_icp_degenerate_inputs(velo, oracle, calib, params, ctx):
+    """duplicated points (exact distance ties), far-away pose (no correspondences), identity pose (small-angle branch)"""
+    rawS = small_scan(velo, 7)
+    rawM = rawS.copy()
+    rawS = np.concatenate([rawS, rawS[-200:]])            # duplicates inside the last ring: ties broken by lower index
+    ctx.scan_upload(1, rawM); ctx.scan_upload(0, rawS)
+    ptsM, rsM, _ = oracle.segment(rawM, calib)
+    ptsS, rsS, _ = oracle.segment(rawS, calib)
+    for pose in ([0, 0, 0, 0, 0, 0], [1e-9, 0, -1e-9, 0.01, 0, 0.02], [0, 0, 0, 0, 0, 500.0], [0.3, 0.2, -0.4, 1, -2, 3]):
+        _check_icp(velo, oracle, params, ctx, ptsM, rsM, ptsS, rsS, np.array(pose, np.float64), 1, 3, 0)
+
+
+def _visual_inputs(velo, oracle, calib, ctx, F, ncam, frames=(7, 8)):
+    out = {}
+    for slot, f in enumerate(frames):
+        raw, n = velo.synth.scan(f)
+        ctx.scan_upload(slot, raw)
+        pts, rs, _ = oracle.segment(raw, calib)
+        kpA, kpB, m = velo.synth.features(f, F, ncam, 1 if ncam == 4 else 0)
+        hd = np.zeros((2, ncam, F), np.int32); kw = np.zeros((2, ncam, F, 4), np.float32)
+        for cam in range(ncam):
+            ctx.project(slot, cam)
+            rc, proj, valid = oracle.project(pts, rs, calib, cam)
+            for s, kp in enumerate((kpA[cam], kpB[cam])):
+                h, k = oracle.depth_assoc(valid, proj, rc, kp)
+                gh, gk = ctx.depth_assoc(slot, cam, kp, s)
+                assert np.array_equal(h, gh) and k.tobytes() == gk.tobytes()
+                hd[s, cam] = h; kw[s, cam, : len(k)] = k
+        out[f] = (kpA, kpB, m, hd, kw)
+    return out
+
+
+@pytest.mark.parametrize("it", [1, 2])
+def test_visual_residuals_parity(velo, oracle, calib, params, ctx, it):
+    F = 2000
+    d = _visual_inputs(velo, oracle, calib, ctx, F, 2)
+    kpA7, _, _, hd7, kw7 = d[7]
+    _, kpB8, m8, hd8, kw8 = d[8]
+    matches = np.zeros((2, F, 2), np.int32); nm = np.zeros(2, np.int32); cat = []
+    lm_valid = np.zeros((2, F), np.int32); lm_xyz = np.zeros((2, F, 4), np.float32)
+    rng = np.random.default_rng(5)
+    for cam in (0, 1):
+        idx = np.nonzero(m8[cam])[0]
+        nm[cam] = len(idx); matches[cam, : len(idx), 0] = idx; matches[cam, : len(idx), 1] = idx
+        cat.append(matches[cam, : len(idx)])
+        for j in range(0, len(idx), 9):
+            lm_valid[cam, j] = 1; lm_xyz[cam, j] = [rng.normal() * 3, rng.normal(), 8 + rng.uniform() * 10, 1]
+    cat = np.concatenate(cat)
+    pose = velo.synth.pose_guess(8, 3 if it == 2 else 0)
+    for use_lm in (False, True):
+        lmv = lm_valid if use_lm else None
+        lmx = lm_xyz if use_lm else None
+        ob, oneq = oracle.visual(kpB8, kpA7, hd8[1], hd7[0], kw8[1], kw7[0], nm, matches, calib, params, pose, it, lmv, lmx)
+        glv = np.concatenate([lm_valid[c, : nm[c]] for c in (0, 1)]) if use_lm else None
+        glx = np.concatenate([lm_xyz[c, : nm[c]] for c in (0, 1)]) if use_lm else None
+        gb, gneq = ctx.visual_residuals(1, 1, 0, 0, nm, cat, pose, it, glv, glx)
+        assert len(gb) == len(ob) > 1000
+        for f in ("cam", "match", "type", "n_res"):
+            assert np.array_equal(gb[f], ob[f]), f
+        np.testing.assert_allclose(gb["residual"], ob["residual"], rtol=RTOL_RES, atol=1e-12)
+        np.testing.assert_allclose(gb["jacobian"], ob["jacobian"], rtol=RTOL_RES, atol=1e-12)
+        scale = np.abs(oneq[:56]).max()
+        np.testing.assert_allclose(gneq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * scale)
+        assert gneq[56] == oneq[56] and gneq[57] == oneq[57]
+
+
+def test_offroad_rig_four_cameras(velo, oracle, ctx4):
+    """BASELINE configs[3]: 4 cameras, 8k features per image: projection + association parity on every camera"""
+    cal = ctx4.cal
+    raw, n = velo.synth.scan(11)
+    ctx4.scan_upload(0, raw)
+    pts, rs, _ = oracle.segment(raw, cal)
+    kpA, kpB, _ = velo.synth.features(11, 8000, 4, 1)
+    ctx4.project(0, 0)
+    for cam in range(4):
+        rc, proj, valid = ctx4.project_download(0, cam)
+        orc, oproj, ovalid = oracle.project(pts, rs, cal, cam)
+        assert np.array_equal(rc, orc) and proj.tobytes() == oproj.tobytes() and valid.tobytes() == ovalid.tobytes()
+        hd, kpwd = ctx4.depth_assoc(0, cam, kpA[cam], 0)
+        ohd, okpwd = oracle.depth_assoc(ovalid, oproj, orc, kpA[cam])
+        assert np.array_equal(hd, ohd) and kpwd.tobytes() == okpwd.tobytes()
+        assert (hd >= 0).sum() > 2000
+
+
+def test_batched_path_equals_single_frame_path_and_oracle(velo, oracle, calib):
+    """the throughput path (batch_upload / batch_run / batch_download) on 3 scans = 2 frame pairs, full schedule
+    (2 f2f iterations x 3 ICP passes, icp_skip 20 to keep the CPU side quick) vs the oracle's timed-baseline driver."""
+    prm = velo.api.default_params(max_slots=3, max_features=1000, max_matches=1000, icp_skip=20)
+    c = velo.api.Context(prm, calib)
+    try:
+        b = velo.synth.Batch(20, 3, prm)
+        c.batch_upload(0, b)
+        c.batch_run(0, 3)
+        icp = np.zeros((3, b.n_passes, velo.abi.NEQ_STRIDE)); vis = np.zeros((3, b.n_vis, velo.abi.NEQ_STRIDE))
+        hd = np.zeros((3, 2, prm.num_cams, prm.max_features), np.int32); nh = np.zeros((3, 2, prm.num_cams), np.int32)
+        c.batch_download(0, 3, icp, vis, hd, nh)
+        sec, oicp, ovis = oracle.bench_frames(b, prm, calib, threads=2, want_out=True)
+        assert np.all(icp[0] == 0) and np.all(vis[0] == 0)
+        for t in (1, 2):
+            for p in range(b.n_passes):
+                sc = np.abs(oicp[t, p, :56]).max()
+                np.testing.assert_allclose(icp[t, p, :56], oicp[t, p, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
+                assert icp[t, p, 56] == oicp[t, p, 56] and icp[t, p, 58] == oicp[t, p, 58]
+            for it in range(b.n_vis):
+                sc = np.abs(ovis[t, it, :56]).max()
+                np.testing.assert_allclose(vis[t, it, :56], ovis[t, it, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
+                assert vis[t, it, 56] == ovis[t, it, 56]
+        # association results of the batch equal the oracle's
+        for t in range(3):
+            pts, rs, _ = oracle.segment(b.scans[t, : b.n_points[t]], calib)
+            for cam in range(prm.num_cams):
+                rc, proj, valid = oracle.project(pts, rs, calib, cam)
+                for s in range(2):
+                    ohd, _ = oracle.depth_assoc(valid, proj, rc, b.kp[t, s, cam])
+                    assert np.array_equal(hd[t, s, cam], ohd)
+                    assert nh[t, s, cam] == (ohd >= 0).sum()
+        npnt, nr, ptot, st = c.batch_counts(0, 3)
+        assert np.array_equal(npnt, b.n_points) and np.all(nr == 64) and np.all(st == 0) and np.all(ptot > 10000)
+    finally:
+        c.close()
+
+
+def test_round_trip_properties_at_full_size(velo, calib):
+    """size-independent properties at BASELINE size (no oracle): ingest is a permutation of a rigid transform,
+    projection survivors are a subsequence inside the FOV, has_depth is a stable enumeration, JtJ is PSD."""
+    prm = velo.api.default_params(max_slots=2, max_features=2000)
+    c = velo.api.Context(prm, calib)
+    try:
+        rawM, nM = velo.synth.scan(301)
+        rawS, nS = velo.synth.scan(300)
+        c.scan_upload(1, rawM); c.scan_upload(0, rawS)
+        pts, rs = c.scan_download(1)
+        assert len(pts) == nM and rs[0] == 0 and rs[-1] == nM and np.all(np.diff(rs) > 0)
+        # rigid transform preserves pairwise distances of the multiset: compare sorted norms about the velodyne origin
+        T = np.array(list(calib.velo_to_cam), np.float64).reshape(4, 4)
+        back = (pts[:, :3].astype(np.float64) - T[:3, 3]) @ T[:3, :3]
+        assert np.allclose(np.sort(np.linalg.norm(back, axis=1)), np.sort(np.linalg.norm(rawM[:, :3].astype(np.float64), axis=1)), atol=2e-3)
+        c.project(1, 0)
+        rc, proj, valid = c.project_download(1, 0)
+        assert np.all(proj[:, 0] >= calib.min_x[0]) and np.all(proj[:, 0] < calib.max_x[0])
+        assert np.all(proj[:, 1] >= calib.min_y[0]) and np.all(proj[:, 1] < calib.max_y[0])
+        kp = velo.synth.features(301, 2000)[0][0]
+        hd, kpwd = c.depth_assoc(1, 0, kp, 0)
+        hits = hd[hd >= 0]
+        assert np.array_equal(hits, np.arange(len(hits))) and len(kpwd) == len(hits)
+        corr, neq, kept = c.icp_pass(1, 0, velo.synth.pose_guess(301, 0), 1, 1)
+        H = np.zeros((6, 6)); H[np.triu_indices(6)] = neq[:21]; H = H + H.T - np.diag(np.diag(H))
+        assert np.linalg.eigvalsh(H).min() > -1e-9 * np.abs(H).max()
+        k = corr["kept"] == 1
+        assert kept == k.sum() and np.all(corr["np_s_i"][k] != corr["np_s_j"][k])
+        assert np.allclose(np.linalg.norm(corr["normal"][k], axis=1), 1.0, atol=1e-5)
+        # determinism: a second run is byte-identical
+        corr2, neq2, _ = c.icp_pass(1, 0, velo.synth.pose_guess(301, 0), 1, 1)
+        assert corr.tobytes() == corr2.tobytes() and neq.tobytes() == neq2.tobytes()
+    finally:
+        c.close()

@@ -342,3 +342,53 @@ def test_round_trip_properties_at_full_size(velo, calib):
         assert corr.tobytes() == corr2.tobytes() and neq.tobytes() == neq2.tobytes()
     finally:
         c.close()
+
+
+def test_cuda_path_against_golden_fixture(velo, oracle):
+    """tests/golden/velo_golden.npz holds outputs of the reference's own source lines: the CUDA path must reproduce them
+    without any oracle in the loop (indices + f32 geometry bit-exact, f64 residuals 1e-5, normal equations 1e-4)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "velo_golden.npz"))
+    cal = velo.api.calib_from_kitti(gold["P"], gold["Tr"], int(gold["wh"][0]), int(gold["wh"][1]))
+    F = gold["kpA60"].shape[1]
+    prm = velo.api.default_params(max_slots=2, max_features=F, max_matches=F)
+    c = velo.api.Context(prm, cal)
+    try:
+        for slot, f in ((0, 60), (1, 61)):
+            c.scan_upload(slot, gold[f"raw{f}"])
+            pts, rs = c.scan_download(slot)
+            assert np.array_equal(rs, gold[f"rs{f}"]) and pts.tobytes() == gold[f"pts{f}"].tobytes()
+            for cam in (0, 1):
+                c.project(slot, cam)
+                rc, proj, valid = c.project_download(slot, cam)
+                assert np.array_equal(rc, gold[f"rc{f}_{cam}"])
+                assert proj.tobytes() == gold[f"proj{f}_{cam}"].tobytes() and valid.tobytes() == gold[f"valid{f}_{cam}"].tobytes()
+                for s, key in enumerate(("kpA", "kpB")):
+                    hd, kw = c.depth_assoc(slot, cam, gold[f"{key}{f}"][cam], s)
+                    assert np.array_equal(hd, gold[f"hd{f}"][s, cam]) and kw.tobytes() == gold[f"kw{f}"][s, cam, : len(kw)].tobytes()
+        for it, skip in ((1, 1), (2, 1), (1, 4)):
+            corr, neq, kept = c.icp_pass(1, 0, gold[f"icp_pose_{it}_{skip}"], it, skip)
+            g = gold[f"icp_corr_{it}_{skip}"]
+            ck = corr[corr["kept"] == 1]
+            assert len(ck) == len(g) == kept
+            for fld in ("src_ring", "src_idx", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
+                assert np.array_equal(ck[fld], g[fld]), fld
+            assert ck["normal"].tobytes() == g["normal"].tobytes() and ck["v0"].tobytes() == g["v0"].tobytes()
+            np.testing.assert_allclose(ck["residual"], g["residual"], rtol=RTOL_RES, atol=1e-9)
+            np.testing.assert_allclose(ck["jacobian"], g["jacobian"], rtol=RTOL_RES, atol=1e-9)
+            gn = gold[f"icp_neq_{it}_{skip}"]
+            np.testing.assert_allclose(neq[:56], gn[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(gn[:56]).max())
+        nm = gold["vis_nm"]
+        cat = np.concatenate([gold["vis_matches"][cam, : nm[cam]] for cam in (0, 1)])
+        for it in (1, 2):
+            b, neq = c.visual_residuals(1, 1, 0, 0, nm, cat, gold[f"vis_pose_{it}"], it)
+            g = gold[f"vis_blocks_{it}"]
+            assert len(b) == len(g)
+            for fld in ("cam", "match", "type", "n_res"):
+                assert np.array_equal(b[fld], g[fld]), fld
+            np.testing.assert_allclose(b["residual"], g["residual"], rtol=RTOL_RES, atol=1e-12)
+            np.testing.assert_allclose(b["jacobian"], g["jacobian"], rtol=RTOL_RES, atol=1e-12)
+            gn = gold[f"vis_neq_{it}"]
+            np.testing.assert_allclose(neq[:56], gn[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(gn[:56]).max())
+    finally:
+        c.close()

@@ -1,0 +1,36 @@
+"""Frame sharding across GPUs: frames are independent units, so rank g owns the contiguous range
+[g*T/G, (g+1)*T/G) and additionally ingests the one-frame halo `start-1` as ICP target.  No collective is on the
+data path; the only exchange is a host gather of the per-frame normal equations."""
+import numpy as np
+
+
+def frame_range(total_frames, world, rank):
+    """(first frame, number of frames) owned by `rank`; remainders go to the lowest ranks."""
+    base, rem = divmod(total_frames, world)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def halo_range(total_frames, world, rank):
+    """(first scan to ingest, number of scans): the owned frames plus the previous scan."""
+    start, count = frame_range(total_frames, world, rank)
+    return start - 1, count + 1
+
+
+def gather_rows(dist, local, dst=0):
+    """Gather [count_r, ...] arrays of every rank to `dst` (torch.distributed, any backend) and concatenate in
+    rank order.  Returns the concatenation on dst, None elsewhere."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(local))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64))
+    mx = int(max(int(c.item()) for c in counts))
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype)
+    pad[: t.shape[0]] = t
+    out = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, out, dst=dst)
+    if rank != dst:
+        return None
+    return np.concatenate([o[: int(c.item())].numpy() for o, c in zip(out, counts)], axis=0)

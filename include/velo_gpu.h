@@ -145,6 +145,9 @@ const char *velo_gpu_kernel_name(int k);
 /* ScanData ctor (lru.h:12-28): loadPoints layout (kitti.h:121-152) -> segmentPoints (kitti.h:154-185)
  * -> neighbour index (replaces 64x KdTreeFLANN::setInputCloud, lru.h:17-20).  xyzr: n x float4. */
 int  velo_gpu_scan_upload(velo_gpu_ctx *ctx, int slot, const float *xyzr, int n);
+/* same, for a scan that is ALREADY ring-segmented in the cam-0 frame (the `scans` vector of kitti.h:156 flattened):
+ * xyz1 = n x {x,y,z,*}, ring_start[n_rings+1].  Skips segmentPoints, builds the neighbour index. */
+int  velo_gpu_scan_upload_rings(velo_gpu_ctx *ctx, int slot, const float *xyz1, const int *ring_start, int n_rings);
 int  velo_gpu_scan_info(velo_gpu_ctx *ctx, int slot, int *n_points, int *n_rings);
 /* ring-ordered cam-0-frame points (n x {x,y,z,1}) and ring_start[n_rings+1] — the `scans` vector of kitti.h:156 */
 int  velo_gpu_scan_download(velo_gpu_ctx *ctx, int slot, float *xyz1, int *ring_start);
@@ -153,6 +156,10 @@ int  velo_gpu_scan_download(velo_gpu_ctx *ctx, int slot, float *xyz1, int *ring_
 int  velo_gpu_project(velo_gpu_ctx *ctx, int slot, int cam);
 /* ring_count[n_rings]; proj: total x (x,y); valid: total x {x,y,z,1}, rings concatenated in order */
 int  velo_gpu_project_download(velo_gpu_ctx *ctx, int slot, int cam, int *ring_count, float *proj, float *valid, int *total);
+
+/* install an externally computed projection (the `projection` / `scans_valid` arguments of velo.h:377-383) for
+ * (slot, cam): ring_count[n_rings of the slot], proj/valid ring-concatenated; every ring_count[s] <= ring length */
+int  velo_gpu_projection_upload(velo_gpu_ctx *ctx, int slot, int cam, const int *ring_count, const float *proj, const float *valid);
 
 /* featureDepthAssociation (velo.h:377-497): kp = F x (x,y) canonical; has_depth[F]; kpwd = n_hits x {x,y,z,1} */
 int  velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int set, const float *kp, int F,

@@ -392,3 +392,41 @@ def test_cuda_path_against_golden_fixture(velo, oracle):
             np.testing.assert_allclose(neq[:56], gn[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(gn[:56]).max())
     finally:
         c.close()
+
+
+def test_cpp_dropin_header(velo, oracle, calib, params, tmp_path):
+    """include/velo_dropin.hpp (the reference's C++ signatures) compiled with g++ against libvelo_gpu.so and driven like
+    main.cpp drives the reference; outputs compared with the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "vision-enhanced-lidar-odometry_b200")
+    exe = tmp_path / "dropin_main"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "dropin_main.cpp"),
+                    "-L", pkg, "-lvelo_gpu", f"-Wl,-rpath,{pkg}", "-o", str(exe)], check=True)
+    P, Tr, w, h = velo.synth.calib_raw(0)
+    np.concatenate([P, Tr, np.array([w, h], np.float32)]).astype(np.float32).tofile(tmp_path / "calib.bin")
+    raw0, raw1 = small_scan(velo, 7, range(10, 50), 2), small_scan(velo, 8, range(10, 50), 2)
+    raw0.tofile(tmp_path / "scan0.bin"); raw1.tofile(tmp_path / "scan1.bin")
+    kp = velo.synth.features(8, 1500)[0][0]
+    kp.tofile(tmp_path / "kp.bin")
+    pose = velo.synth.pose_guess(8, 0)
+    pose.tofile(tmp_path / "pose.bin")
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    pts1, rs1, _ = oracle.segment(raw1, calib)
+    pts0, rs0, _ = oracle.segment(raw0, calib)
+    for cam in (0, 1):
+        rc, proj, valid = oracle.project(pts1, rs1, calib, cam)
+        assert np.array_equal(np.fromfile(tmp_path / f"out_rc{cam}.bin", np.int32), rc)
+        assert np.fromfile(tmp_path / f"out_proj{cam}.bin", np.float32).tobytes() == proj.tobytes()
+        hd, kw = oracle.depth_assoc(valid, proj, rc, kp)
+        assert np.array_equal(np.fromfile(tmp_path / f"out_hd{cam}.bin", np.int32), hd)
+        assert np.fromfile(tmp_path / f"out_kpwd{cam}.bin", np.float32).tobytes() == kw.tobytes()
+        assert (hd >= 0).sum() > 100
+    corr = np.fromfile(tmp_path / "out_corr.bin", velo.abi.ICP_CORR_DTYPE)
+    ocorr, oneq, okept = oracle.icp_pass(pts1, rs1, pts0, rs0, pose, 1, 5, params, 1)
+    for f in ("src_ring", "src_idx", "kept", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
+        assert np.array_equal(corr[f], ocorr[f]), f
+    neq = np.fromfile(tmp_path / "out_neq.bin", np.float64)
+    np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max())

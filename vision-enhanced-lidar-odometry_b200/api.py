@@ -45,6 +45,8 @@ def lib():
     L.velo_gpu_profile_enable.argtypes = [_P, C.c_int]
     L.velo_gpu_profile_read.argtypes = [_P, _P, _P]
     L.velo_gpu_scan_upload.argtypes = [_P, C.c_int, _P, C.c_int]
+    L.velo_gpu_scan_upload_rings.argtypes = [_P, C.c_int, _P, _P, C.c_int]
+    L.velo_gpu_projection_upload.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
     L.velo_gpu_scan_info.argtypes = [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.velo_gpu_scan_download.argtypes = [_P, C.c_int, _P, _P]
     L.velo_gpu_project.argtypes = [_P, C.c_int, C.c_int]
@@ -184,6 +186,16 @@ class Context:
     def scan_upload(self, slot, xyzr):
         xyzr = np.ascontiguousarray(xyzr, np.float32).reshape(-1, 4)
         self._ck(self.L.velo_gpu_scan_upload(self.h, slot, _ptr(xyzr), len(xyzr)))
+
+    def scan_upload_rings(self, slot, xyz1, ring_start):
+        xyz1 = np.ascontiguousarray(xyz1, np.float32).reshape(-1, 4)
+        ring_start = np.ascontiguousarray(ring_start, np.int32)
+        self._ck(self.L.velo_gpu_scan_upload_rings(self.h, slot, _ptr(xyz1), _ptr(ring_start), len(ring_start) - 1))
+
+    def projection_upload(self, slot, cam, ring_count, proj, valid):
+        ring_count = np.ascontiguousarray(ring_count, np.int32)
+        proj = np.ascontiguousarray(proj, np.float32); valid = np.ascontiguousarray(valid, np.float32)
+        self._ck(self.L.velo_gpu_projection_upload(self.h, slot, cam, _ptr(ring_count), _ptr(proj), _ptr(valid)))
 
     def scan_info(self, slot):
         a, b = C.c_int(), C.c_int()

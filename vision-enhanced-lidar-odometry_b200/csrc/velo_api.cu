@@ -339,6 +339,30 @@ extern "C" int velo_gpu_scan_upload(velo_gpu_ctx *ctx, int slot, const float *xy
     return VELO_OK;
 }
 
+extern "C" int velo_gpu_scan_upload_rings(velo_gpu_ctx *ctx, int slot, const float *xyz1, const int *ring_start, int n_rings) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot)) return VELO_ERR_INVALID_ARG;
+    if (n_rings < 0 || !ring_start || ring_start[0] != 0) return fail(ctx, VELO_ERR_INVALID_ARG, "bad ring_start");
+    if (n_rings > ctx->B.R) return fail(ctx, VELO_ERR_CAPACITY, "more rings than max_rings");
+    for (int s = 0; s < n_rings; s++) if (ring_start[s + 1] < ring_start[s]) return fail(ctx, VELO_ERR_INVALID_ARG, "ring_start must be non-decreasing");
+    const int n = ring_start[n_rings];
+    if (n > ctx->prm.max_points) return fail(ctx, VELO_ERR_CAPACITY, "scan has more points than max_points");
+    if (n > 0 && !xyz1) return fail(ctx, VELO_ERR_INVALID_ARG, "null points");
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const int zero = 0;
+    if (n > 0) CK(cudaMemcpyAsync(B.pts + (size_t)slot * B.N, xyz1, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.ring_start + (size_t)slot * (B.R + 1), ring_start, (size_t)(n_rings + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.n_points + slot, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.n_rings + slot, &n_rings, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.status + slot, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_npoints[slot] = n;
+    launch_index(launcher(ctx), B, ctx->dcal, slot, 1);
+    CK(cudaGetLastError());
+    return VELO_OK;
+}
+
 extern "C" int velo_gpu_scan_info(velo_gpu_ctx *ctx, int slot, int *n_points, int *n_rings) {
     if (!ctx) return VELO_ERR_INVALID_ARG;
     if (check_slot(ctx, slot)) return VELO_ERR_INVALID_ARG;
@@ -396,6 +420,28 @@ extern "C" int velo_gpu_project_download(velo_gpu_ctx *ctx, int slot, int cam, i
     }
     CK(cudaStreamSynchronize(ctx->stream));
     if (total) *total = o;
+    return VELO_OK;
+}
+
+extern "C" int velo_gpu_projection_upload(velo_gpu_ctx *ctx, int slot, int cam, const int *ring_count, const float *proj, const float *valid) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_cam(ctx, cam) || !ring_count) return fail(ctx, VELO_ERR_INVALID_ARG, "bad camera / ring_count");
+    int np, nr; int st = velo_gpu_scan_info(ctx, slot, &np, &nr); if (st) return st;
+    const DevBuffers &B = ctx->B;
+    std::vector<int> rs(nr + 1, 0);
+    if (nr > 0) { CK(cudaMemcpyAsync(rs.data(), B.ring_start + (size_t)slot * (B.R + 1), (nr + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    size_t o = 0;
+    for (int s = 0; s < nr; s++) {
+        if (ring_count[s] < 0 || ring_count[s] > rs[s + 1] - rs[s]) return fail(ctx, VELO_ERR_INVALID_ARG, "ring_count exceeds the ring length");
+        if (ring_count[s] > 0) {
+            if (!proj || !valid) return fail(ctx, VELO_ERR_INVALID_ARG, "null projection arrays");
+            CK(cudaMemcpyAsync(B.proj + ((size_t)slot * B.C + cam) * B.N + rs[s], proj + 2 * o, ring_count[s] * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(B.valid + ((size_t)slot * B.C + cam) * B.N + rs[s], valid + 4 * o, ring_count[s] * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        o += ring_count[s];
+    }
+    if (nr > 0) CK(cudaMemcpyAsync(B.proj_count + ((size_t)slot * B.C + cam) * B.R, ring_count, nr * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return VELO_OK;
 }
 

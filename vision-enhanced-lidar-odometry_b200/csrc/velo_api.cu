@@ -170,7 +170,7 @@ void make_pose_pack(const double pose[6], PosePack *P) {
 
 // ------------------------------------------------------------------------------------------------ profiling hooks
 static const char *k_names[VELO_NUM_KERNELS] = { "ingest_flags", "ingest_rings", "ingest_permute", "index_build", "project_occlude",
-                                                 "assoc_search", "assoc_compact", "icp_pass", "neq_reduce", "visual_residuals", "misc0", "misc1" };
+                                                 "assoc_search", "assoc_compact", "icp_pass", "neq_reduce", "visual_residuals", "index_masks", "misc1" };
 extern "C" const char *velo_gpu_kernel_name(int k) { return (k >= 0 && k < VELO_NUM_KERNELS) ? k_names[k] : ""; }
 
 static cudaEvent_t get_event(velo_gpu_ctx *c) {
@@ -228,7 +228,9 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &B.n_points, S)); CKC(dalloc(ctx, &B.n_rings, S)); CKC(dalloc(ctx, &B.ring_start, S * (R + 1))); CKC(dalloc(ctx, &B.status, S));
     CKC(dalloc(ctx, &B.pts, S * N)); CKC(dalloc(ctx, &B.sorted, S * N));
     CKC(dalloc(ctx, &B.cell_start, S * R * (VELO_AZ_BINS + 1))); CKC(dalloc(ctx, &B.sec_elev, S * R * VELO_SECTORS));
-    CKC(dalloc(ctx, &B.proj, S * C * N)); CKC(dalloc(ctx, &B.valid, S * C * N)); CKC(dalloc(ctx, &B.proj_count, S * C * R));
+    B.W = (B.R + 63) / 64;
+    CKC(dalloc(ctx, &B.mask_lo, S * VELO_SECTORS * VELO_EL_BUCKETS * (size_t)B.W)); CKC(dalloc(ctx, &B.mask_hi, S * VELO_SECTORS * VELO_EL_BUCKETS * (size_t)B.W));
+    CKC(dalloc(ctx, &B.proj, S * C * N)); CKC(dalloc(ctx, &B.valid, S * C * N)); CKC(dalloc(ctx, &B.proj_count, S * C * R)); CKC(dalloc(ctx, &B.proj_yrange, S * C * R));
     const size_t SK = S * VELO_NUM_KP_SETS * C;
     CKC(dalloc(ctx, &B.kp, SK * F)); CKC(dalloc(ctx, &B.n_kp, SK)); CKC(dalloc(ctx, &B.has_depth, SK * F)); CKC(dalloc(ctx, &B.kpwd, SK * F));
     CKC(dalloc(ctx, &B.n_hits, SK)); CKC(dalloc(ctx, &B.hit_tmp, SK * F)); CKC(dalloc(ctx, &B.kpwd_tmp, SK * F));
@@ -440,7 +442,17 @@ extern "C" int velo_gpu_projection_upload(velo_gpu_ctx *ctx, int slot, int cam, 
         }
         o += ring_count[s];
     }
-    if (nr > 0) CK(cudaMemcpyAsync(B.proj_count + ((size_t)slot * B.C + cam) * B.R, ring_count, nr * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float2> yr(nr > 0 ? nr : 1);
+    o = 0;
+    for (int s = 0; s < nr; s++) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int i = 0; i < ring_count[s]; i++) { const float y = proj[2 * (o + i) + 1]; lo = fminf(lo, y); hi = fmaxf(hi, y); }
+        yr[s] = make_float2(lo, hi); o += ring_count[s];
+    }
+    if (nr > 0) {
+        CK(cudaMemcpyAsync(B.proj_count + ((size_t)slot * B.C + cam) * B.R, ring_count, nr * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.proj_yrange + ((size_t)slot * B.C + cam) * B.R, yr.data(), nr * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return VELO_OK;
 }
@@ -472,6 +484,7 @@ static void fill_icp_unit(const velo_gpu_ctx *ctx, IcpUnit *u, int src, int tgt,
     u->src_slot = src; u->tgt_slot = tgt; u->iter = iter; u->skip = skip;
     const double thr = ctx->prm.correspondence_thresh_icp / iter / iter / iter / iter;     // velo.h:829
     u->thr_f = floor_to_float(thr);
+    u->thr_excl = nextafterf(u->thr_f, INFINITY);
     u->norm_thr_f = ceil_to_float(ctx->prm.icp_norm_condition);                            // velo.h:873
     u->loss_a = ctx->prm.loss_thresh_3DPD; u->weight = ctx->prm.weight_3DPD;               // velo.h:885-891
     make_pose_pack(pose, &u->pose);

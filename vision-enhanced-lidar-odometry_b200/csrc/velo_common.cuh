@@ -44,6 +44,10 @@ __device__ __forceinline__ void idx_frame(const DevCalib &cal, float x, float y,
     vy = cal.vtc[1] * dx + cal.vtc[5] * dy + cal.vtc[9] * dz;
     vz = cal.vtc[2] * dx + cal.vtc[6] * dy + cal.vtc[10] * dz;
 }
+__device__ __forceinline__ int el_bucket(float el) {   // monotone non-decreasing in el (required for conservative masks)
+    int b = (int)floorf((el - VELO_EL_MIN) * (VELO_EL_BUCKETS / (VELO_EL_MAX - VELO_EL_MIN)));
+    return min(max(b, 0), VELO_EL_BUCKETS - 1);
+}
 __device__ __forceinline__ int az_bin(float az) {
     int b = (int)((az + CUDART_PI_F) * (VELO_AZ_BINS / (2.0f * CUDART_PI_F)));
     return min(max(b, 0), VELO_AZ_BINS - 1);

@@ -10,9 +10,10 @@
 //   sorted     float4 [S][N]          per ring counting-sorted by azimuth bin, .w = index in ring (int bits)
 //   cell_start int    [S][R][AZ+1]    start of (ring, azimuth bin) in `sorted` (slot-relative)
 //   sec_elev   float2 [S][R][SEC]     elevation interval of the ring inside one azimuth sector (AZ/SEC bins)
+//   mask_lo/hi u64    [S][SEC][EL][W] cumulative ring bit masks over elevation buckets (W = ceil(R/64) words)
 //   proj       float2 [S][C][N]       canonical projection, ring r at offset ring_start[r] (velo.h:366)
 //   valid      float4 [S][C][N]       matching cam-0 points (velo.h:368)
-//   proj_count int    [S][C][R]
+//   proj_count int    [S][C][R],  proj_yrange float2 [S][C][R] (y range of the ring's projections, prunes the association)
 //   kp         float2 [S][2][C][F]    keypoints (set 0 = detected, set 1 = tracked)
 //   has_depth  int    [S][2][C][F],  kpwd float4 [S][2][C][F],  n_hits int [S][2][C]   (velo.h:377-497)
 #pragma once
@@ -24,12 +25,15 @@
 #define VELO_SECTORS 64
 #define VELO_BINS_PER_SECTOR (VELO_AZ_BINS / VELO_SECTORS)
 #define VELO_MAX_RINGS_HARD 256
+#define VELO_EL_BUCKETS 128         /* elevation buckets of the ring-mask tables */
+#define VELO_EL_MIN (-0.62f)        /* rad; elevations outside [EL_MIN, EL_MAX] clamp to the edge buckets (still conservative) */
+#define VELO_EL_MAX (0.34f)
 #define VELO_IDX_BITS 20            /* index-in-ring bits of the neighbour key */
 #define VELO_RING_BITS 12
 
 enum {
     VK_INGEST_FLAGS = 0, VK_INGEST_RINGS, VK_INGEST_PERMUTE, VK_INDEX_BUILD, VK_PROJECT, VK_ASSOC_SEARCH,
-    VK_ASSOC_COMPACT, VK_ICP_PASS, VK_NEQ_REDUCE, VK_VISUAL, VK_MISC0, VK_MISC1
+    VK_ASSOC_COMPACT, VK_ICP_PASS, VK_NEQ_REDUCE, VK_VISUAL, VK_INDEX_MASKS, VK_MISC1
 };
 
 // calibration packed for kernel parameters
@@ -46,7 +50,8 @@ struct DevBuffers {
     int S, N, R, C, F, MM, P;
     float4 *raw; uint32_t *flagbits; int *n_points; int *n_rings; int *ring_start; int *status;
     float4 *pts; float4 *sorted; int *cell_start; float2 *sec_elev;
-    float2 *proj; float4 *valid; int *proj_count;
+    unsigned long long *mask_lo, *mask_hi; int W;   // [S][SEC][EL_BUCKETS][W]: rings with bucket(lo) <= b / bucket(hi) >= b
+    float2 *proj; float4 *valid; int *proj_count; float2 *proj_yrange;
     float2 *kp; int *n_kp; int *has_depth; float4 *kpwd; int *n_hits; int *hit_tmp; float4 *kpwd_tmp;
     int *matches; int *n_matches;
 };
@@ -66,6 +71,7 @@ struct IcpUnit {
     int iter, skip;
     float thr_f;              // largest float f with (double)f <= correspondence_thresh_icp/iter^4 (velo.h:829)
     float norm_thr_f;         // smallest float f with (double)f >= icp_norm_condition (velo.h:873)
+    float thr_excl, pad0;     // smallest float above thr_f (exclusive bound of the candidate loop)
     double loss_a;            // loss_thresh_3DPD
     double weight;            // weight_3DPD
     PosePack pose;

@@ -52,25 +52,27 @@ __device__ __forceinline__ Window make_window(float d2b, float az, float D, floa
     return w;
 }
 
-// min key over sorted[start, end) of ring s
-__device__ __forceinline__ u64 scan_range(const float4 *__restrict__ sorted, int start, int end, int s, float mx, float my, float mz, float thr_f, u64 best) {
+// nearest candidate of one ring inside sorted[start, end): smallest d2, ties -> lower index in ring.
+// bd starts at the smallest float above the threshold and bi at -1, so `d2 < bd` also applies the threshold (velo.h:829).
+__device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, int start, int end, float mx, float my, float mz, float &bd, int &bi) {
 #pragma unroll 4
     for (int p = start; p < end; p++) {
         const float4 c = __ldg(sorted + p);
         const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
-        if (d2 <= thr_f) { const u64 k = make_key(d2, s, __float_as_int(c.w)); if (k < best) best = k; }
+        const int idx = __float_as_int(c.w);
+        if (d2 < bd) { bd = d2; bi = idx; }
+        else if (d2 == bd && idx < bi) bi = idx;
     }
-    return best;
 }
 __device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, const int *__restrict__ cs, int s, const Window &w,
-                                         float mx, float my, float mz, float thr_f) {
-    u64 best = KEY_INF;
-    if (!w.wrapped) best = scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), s, mx, my, mz, thr_f, best);
+                                         float mx, float my, float mz, float thr_excl) {
+    float bd = thr_excl; int bi = -1;
+    if (!w.wrapped) scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi);
     else {
-        best = scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), s, mx, my, mz, thr_f, best);
-        best = scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), s, mx, my, mz, thr_f, best);
+        scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), mx, my, mz, bd, bi);
+        scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi);
     }
-    return best;
+    return bi >= 0 ? make_key(bd, s, bi) : KEY_INF;
 }
 // elevation gap between el and the ring's interval over the sectors touched by the window
 __device__ __forceinline__ float ring_gap(const float2 *__restrict__ se, const Window &w, float el) {
@@ -84,6 +86,18 @@ __device__ __forceinline__ float ring_gap(const float2 *__restrict__ se, const W
     }
     return fmaxf(fmaxf(lo - el, el - hi), 0.0f);   // +inf when the sectors are empty
 }
+// candidate rings (64-ring word `word`) whose elevation interval in a sector of the window can come within w.gam of el
+__device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 *__restrict__ mhi, int W, int word, const Window &w, float el) {
+    const int e0 = el_bucket(el - w.gam), e1 = el_bucket(el + w.gam);
+    int sa = w.b0 / VELO_BINS_PER_SECTOR, sb = w.b1 / VELO_BINS_PER_SECTOR;
+    if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
+    u64 m = 0ull;
+    for (int sec = sa;; sec = (sec + 1) & (VELO_SECTORS - 1)) {
+        m |= __ldg(mlo + ((size_t)sec * VELO_EL_BUCKETS + e1) * W + word) & __ldg(mhi + ((size_t)sec * VELO_EL_BUCKETS + e0) * W + word);
+        if (sec == sb) break;
+    }
+    return m;
+}
 
 // grid = (ctas per unit, n_units); one thread = one query at a time
 __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
@@ -93,6 +107,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     __shared__ double s_rows[ICP_THREADS / 32][32 * NEQ_ROW];
     __shared__ double s_red[(ICP_THREADS / 32) * 56];
     __shared__ int s_kept;
+    __shared__ PosePack s_P;
     const IcpUnit &U = units[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (U.src_slot < 0) {   // unit without a previous scan: contributes nothing
@@ -103,6 +118,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     const int *rsM = B.ring_start + (size_t)U.src_slot * (B.R + 1);
     const int *rsS = B.ring_start + (size_t)U.tgt_slot * (B.R + 1);
     const int skip = U.skip;
+    for (int i = tid; i < (int)(sizeof(PosePack) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(&s_P)[i] = reinterpret_cast<const double *>(&U.pose)[i];
     if (tid == 0) {
         int q = 0; s_kept = 0;
         for (int s = 0; s < nrM; s++) { s_q[s] = q; int r0 = rsM[s], L = rsM[s + 1] - r0; s_rsM[s] = r0; q += (L + skip - 1) / skip; }
@@ -117,8 +134,11 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
     const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
     const float2 *seS = B.sec_elev + (size_t)U.tgt_slot * B.R * VELO_SECTORS;
-    const PosePack &P = U.pose;
-    const float thr_f = U.thr_f;
+    const int W = B.W;
+    const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
+    const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
+    const PosePack &P = s_P;
+    const float thr_f = U.thr_f, thr_excl = U.thr_excl;
     double acc = 0.0, raw = 0.0;
     int kept_local = 0;
 
@@ -157,32 +177,42 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
             float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
             const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
             const float az = atan2f(vy, vx), el = atan2f(vz, D);
-            const int bq = az_bin(az), secq = bq / VELO_BINS_PER_SECTOR;
+            const int bq = az_bin(az);
 
             u64 ki = KEY_INF, kj = KEY_INF;
-            // seeds: the two rings closest in elevation, 3 azimuth bins each -> a tight bound before the exhaustive pass
+            // seeds: up to 3 rings whose elevation interval is within SEED_GAM of the query, +-1 azimuth bin each
+            // -> a tight bound before the exhaustive pass (any real point gives a valid bound)
             {
-                float g0 = CUDART_INF_F, g1 = CUDART_INF_F; int s0 = -1, s1 = -1;
-                for (int s = 0; s < nrS; s++) {
-                    const float2 e = __ldg(seS + s * VELO_SECTORS + secq);
-                    const float g = fmaxf(fmaxf(e.x - el, el - e.y), 0.0f);
-                    if (g < g0) { g1 = g0; s1 = s0; g0 = g; s0 = s; } else if (g < g1) { g1 = g; s1 = s; }
-                }
-                Window ws; ws.full = false; ws.wrapped = false; ws.gam = 0.f;
+                Window ws; ws.full = false; ws.wrapped = false; ws.gam = 0.0065f;
                 ws.b0 = max(bq - 1, 0); ws.b1 = min(bq + 1, VELO_AZ_BINS - 1);
-                if (s0 >= 0) merge_key(scan_ring(sorted, csS + s0 * (VELO_AZ_BINS + 1), s0, ws, mx, my, mz, thr_f), ki, kj);
-                if (s1 >= 0) merge_key(scan_ring(sorted, csS + s1 * (VELO_AZ_BINS + 1), s1, ws, mx, my, mz, thr_f), ki, kj);
+                int seeds = 0;
+                for (int word = 0; word < W && seeds < 3; word++) {
+                    u64 m = ring_mask(mloS, mhiS, W, word, ws, el);
+                    while (m && seeds < 3) {
+                        const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; seeds++;
+                        merge_key(scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, ws, mx, my, mz, thr_excl), ki, kj);
+                    }
+                }
             }
-            // exhaustive pass over all rings, pruned by the current bound on d2_j (velo.h:825-848)
+            // exhaustive pass, pruned by the current bound on d2_j (velo.h:825-848): only rings in the mask can hold a
+            // point within the bound; each is visited once (the mask only shrinks when the bound does)
             float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
             Window w = make_window(bound, az, D, rho);
-            for (int s = 0; s < nrS; s++) {
-                if (ring_gap(seS + s * VELO_SECTORS, w, el) > w.gam) continue;
-                const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, w, mx, my, mz, thr_f);
-                if (k == KEY_INF) continue;
-                const u64 oj = kj;
-                merge_key(k, ki, kj);
-                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+            for (int word = 0; word < W; word++) {
+                u64 m = ring_mask(mloS, mhiS, W, word, w, el), done = 0ull;
+                while (m) {
+                    const int bit = __ffsll((long long)m) - 1; m &= m - 1; done |= 1ull << bit;
+                    const int s = word * 64 + bit;
+                    if (ring_gap(seS + s * VELO_SECTORS, w, el) > w.gam) continue;
+                    const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, w, mx, my, mz, thr_excl);
+                    if (k == KEY_INF) continue;
+                    const u64 oj = kj;
+                    merge_key(k, ki, kj);
+                    if (kj != oj) {
+                        bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho);
+                        m = ring_mask(mloS, mhiS, W, word, w, el) & ~done;
+                    }
+                }
             }
 
             velo_icp_corr rec;

@@ -131,6 +131,29 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
     }
 }
 
+// Ring-mask tables: for (slot, sector, elevation bucket b)  mask_lo = { rings r : bucket(lo_r) <= b },  mask_hi = { r : bucket(hi_r) >= b }.
+// The rings whose elevation interval in that sector can intersect [e0, e1] are a subset of mask_lo[bucket(e1)] & mask_hi[bucket(e0)]
+// (bucket() is monotone), which turns the per-query 64-ring scan into two 8-byte loads per sector.
+__global__ void __launch_bounds__(VELO_EL_BUCKETS) k_index_masks(DevBuffers B, int slot0) {
+    const int slot = slot0 + blockIdx.y, sec = blockIdx.x, b = threadIdx.x;
+    const int nr = B.n_rings[slot];
+    const float2 *se = B.sec_elev + (size_t)slot * B.R * VELO_SECTORS + sec;
+    unsigned long long *mlo = B.mask_lo + (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
+    unsigned long long *mhi = B.mask_hi + (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
+    for (int w = 0; w < B.W; w++) {
+        unsigned long long lo = 0ull, hi = 0ull;
+        const int r1 = min(nr, (w + 1) * 64);
+        for (int r = w * 64; r < r1; r++) {
+            const float2 e = se[(size_t)r * VELO_SECTORS];
+            if (e.x <= e.y) {                                   // sector not empty for this ring
+                if (el_bucket(e.x) <= b) lo |= 1ull << (r & 63);
+                if (el_bucket(e.y) >= b) hi |= 1ull << (r & 63);
+            }
+        }
+        mlo[w] = lo; mhi[w] = hi;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ a5: projection
 // One warp per (ring, slot), all cameras.  Lanes project + FOV-test 32 points at a time; lane `cam` then runs
 // the reference's sequential occlusion stack (velo.h:351-368) over the survivors of its camera.  The stack IS
@@ -148,6 +171,7 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DevBuffers B, DevCa
     const int C = cal.num_cams;
     // per-camera stack state lives in lane == cam
     int depth = 0; float top_x = 0.f, top_z = 0.f;
+    float ylo = CUDART_INF_F, yhi = -CUDART_INF_F;      // y range of everything ever pushed (superset of the final stack)
     float2 *proj = nullptr; float4 *valid = nullptr; float tz = 0.f;
     if (lane < C) {
         proj = B.proj + ((size_t)slot * B.C + lane) * B.N + r0;
@@ -178,7 +202,9 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DevBuffers B, DevCa
                     if (depth > 0) { top_x = proj[depth - 1].x; top_z = __fadd_rn(valid[depth - 1].z, tz); }
                 }
                 if (depth > 0 && cx < top_x && ppz > top_z) continue;      // velo.h:360-365: skip occluded
-                proj[depth] = make_float2(cx, s_c[wid][lane][1][b]);        // velo.h:366-368
+                const float cy = s_c[wid][lane][1][b];
+                ylo = fminf(ylo, cy); yhi = fmaxf(yhi, cy);
+                proj[depth] = make_float2(cx, cy);                          // velo.h:366-368
                 float4 q = s_p[wid][b]; q.w = 1.0f;
                 valid[depth] = q;
                 depth++; top_x = cx; top_z = ppz;
@@ -186,7 +212,10 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DevBuffers B, DevCa
         }
         __syncwarp();
     }
-    if (lane < C) B.proj_count[((size_t)slot * B.C + lane) * B.R + ring] = depth;
+    if (lane < C) {
+        B.proj_count[((size_t)slot * B.C + lane) * B.R + ring] = depth;
+        B.proj_yrange[((size_t)slot * B.C + lane) * B.R + ring] = make_float2(ylo, yhi);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ a6/a7: depth association
@@ -211,6 +240,7 @@ __device__ __forceinline__ bool width_ok(float dx, const DevCalib &cal) {   // h
 __global__ void __launch_bounds__(128) k_assoc_search(DevBuffers B, DevCalib cal, int slot0, int set0, int nsets, int cam0) {
     __shared__ int s_rs[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_cnt[VELO_MAX_RINGS_HARD];
+    __shared__ float2 s_yr[VELO_MAX_RINGS_HARD];
     const int cam = cam0 + blockIdx.y;
     const int slot = slot0 + blockIdx.z / nsets, set = set0 + blockIdx.z % nsets;
     const int nr = B.n_rings[slot];
@@ -219,7 +249,8 @@ __global__ void __launch_bounds__(128) k_assoc_search(DevBuffers B, DevCalib cal
     if ((int)(blockIdx.x * blockDim.x) >= F) return;
     const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
     const int *pc = B.proj_count + ((size_t)slot * B.C + cam) * B.R;
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) { s_rs[i] = rs[i]; s_cnt[i] = pc[i]; }
+    const float2 *yr = B.proj_yrange + ((size_t)slot * B.C + cam) * B.R;
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) { s_rs[i] = rs[i]; s_cnt[i] = pc[i]; s_yr[i] = yr[i]; }
     __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= F) return;
@@ -228,7 +259,17 @@ __global__ void __launch_bounds__(128) k_assoc_search(DevBuffers B, DevCalib cal
     const float2 kp = B.kp[sc * B.F + k];
     int last = -1, hit = 0;
     float4 out = make_float4(0.f, 0.f, 0.f, 1.0f);
+    // A hit on the ring pair (s-1, s) needs (proj[s][mid].y > kp.y) != (proj[s-1][last].y > kp.y) (velo.h:414-415): impossible
+    // when both rings lie entirely above (y > kp.y everywhere) or entirely not-above.  A ring whose two pairs are both
+    // impossible cannot influence the result, so its binary search is skipped (its `last` is never consulted).
+    bool ab_prev = true, be_prev = true;             // ring -1: both flags set => pair impossible
+    bool ab_cur = nr > 0 ? (s_yr[0].x > kp.y) : true, be_cur = nr > 0 ? (s_yr[0].y <= kp.y) : true;
     for (int s = 0; s < nr; s++) {
+        const bool ab_next = (s + 1 < nr) ? (s_yr[s + 1].x > kp.y) : true, be_next = (s + 1 < nr) ? (s_yr[s + 1].y <= kp.y) : true;
+        const bool pair_prev = !((ab_prev && ab_cur) || (be_prev && be_cur));
+        const bool pair_next = !((ab_cur && ab_next) || (be_cur && be_next));
+        ab_prev = ab_cur; be_prev = be_cur; ab_cur = ab_next; be_cur = be_next;
+        if (!pair_prev && !pair_next) { last = -1; continue; }
         const int cnt = s_cnt[s];
         if (cnt <= 1) { last = -1; continue; }                       // velo.h:400-403
         const float2 *ps = proj + s_rs[s];
@@ -300,6 +341,8 @@ void launch_ingest(const Launcher &L, const DevBuffers &B, const DevCalib &cal, 
 void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count) {
     dim3 g(B.R, count);
     PRE(VK_INDEX_BUILD); k_index_build<<<g, 256, 0, L.stream>>>(B, cal, slot0); POST(VK_INDEX_BUILD);
+    dim3 g2(VELO_SECTORS, count);
+    PRE(VK_INDEX_MASKS); k_index_masks<<<g2, VELO_EL_BUCKETS, 0, L.stream>>>(B, slot0); POST(VK_INDEX_MASKS);
 }
 void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count) {
     dim3 g((B.R + PROJ_WARPS - 1) / PROJ_WARPS, count);

@@ -30,7 +30,7 @@ extern "C" {
 #define VELO_MAX_CAMS 4          /* kitti.h:4  num_cams_actual */
 #define VELO_NUM_KP_SETS 2       /* main.cpp:261 (after tracking) and main.cpp:600 (after detection) */
 #define VELO_NEQ 28              /* 21 upper-triangular JtJ + 6 Jtr + 1 cost */
-#define VELO_NEQ_STRIDE 64       /* doubles per normal-equation record: [0,28) robustified, [28,56) raw, [56] n_blocks, [57] n_residuals, [58] n_queries */
+#define VELO_NEQ_STRIDE 64       /* doubles per normal-equation record: [0,28) robustified, [28,56) raw, [56] n_blocks, [57] n_residuals, [58] n_queries, ICP only: [59] seed candidates, [60] exhaustive candidates, [61] rings scanned, [62] rings considered */
 
 typedef enum velo_status {
     VELO_OK = 0,

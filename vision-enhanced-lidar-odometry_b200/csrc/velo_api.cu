@@ -227,7 +227,7 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &B.raw, S * N)); CKC(dalloc(ctx, &B.flagbits, S * (N / 32)));
     CKC(dalloc(ctx, &B.n_points, S)); CKC(dalloc(ctx, &B.n_rings, S)); CKC(dalloc(ctx, &B.ring_start, S * (R + 1))); CKC(dalloc(ctx, &B.status, S));
     CKC(dalloc(ctx, &B.pts, S * N)); CKC(dalloc(ctx, &B.sorted, S * N));
-    CKC(dalloc(ctx, &B.cell_start, S * R * (VELO_AZ_BINS + 1))); CKC(dalloc(ctx, &B.sec_elev, S * R * VELO_SECTORS));
+    CKC(dalloc(ctx, &B.cell_start, S * R * (VELO_AZ_BINS + 1))); CKC(dalloc(ctx, &B.sec_box, S * R * VELO_SECTORS));
     B.W = (B.R + 63) / 64;
     CKC(dalloc(ctx, &B.mask_lo, S * VELO_SECTORS * VELO_EL_BUCKETS * (size_t)B.W)); CKC(dalloc(ctx, &B.mask_hi, S * VELO_SECTORS * VELO_EL_BUCKETS * (size_t)B.W));
     CKC(dalloc(ctx, &B.proj, S * C * N)); CKC(dalloc(ctx, &B.valid, S * C * N)); CKC(dalloc(ctx, &B.proj_count, S * C * R)); CKC(dalloc(ctx, &B.proj_yrange, S * C * R));

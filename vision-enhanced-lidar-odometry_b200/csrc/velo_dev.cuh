@@ -9,7 +9,7 @@
 //   pts        float4 [S][N]          ring-ordered cam-0 frame {x,y,z,1}               (kitti.h:154-185)
 //   sorted     float4 [S][N]          per ring counting-sorted by azimuth bin, .w = index in ring (int bits)
 //   cell_start int    [S][R][AZ+1]    start of (ring, azimuth bin) in `sorted` (slot-relative)
-//   sec_elev   float2 [S][R][SEC]     elevation interval of the ring inside one azimuth sector (AZ/SEC bins)
+//   sec_box    float4 [S][R][SEC]     {elev lo, elev hi, range min, range max} of the ring inside one azimuth sector
 //   mask_lo/hi u64    [S][SEC][EL][W] cumulative ring bit masks over elevation buckets (W = ceil(R/64) words)
 //   proj       float2 [S][C][N]       canonical projection, ring r at offset ring_start[r] (velo.h:366)
 //   valid      float4 [S][C][N]       matching cam-0 points (velo.h:368)
@@ -49,7 +49,7 @@ struct DevCalib {
 struct DevBuffers {
     int S, N, R, C, F, MM, P;
     float4 *raw; uint32_t *flagbits; int *n_points; int *n_rings; int *ring_start; int *status;
-    float4 *pts; float4 *sorted; int *cell_start; float2 *sec_elev;
+    float4 *pts; float4 *sorted; int *cell_start; float4 *sec_box;
     unsigned long long *mask_lo, *mask_hi; int W;   // [S][SEC][EL_BUCKETS][W]: rings with bucket(lo) <= b / bucket(hi) >= b
     float2 *proj; float4 *valid; int *proj_count; float2 *proj_yrange;
     float2 *kp; int *n_kp; int *has_depth; float4 *kpwd; int *n_hits; int *hit_tmp; float4 *kpwd_tmp;

@@ -32,59 +32,90 @@ __device__ __forceinline__ void merge_key(u64 k, u64 &ki, u64 &kj) {
     else if (k < kj) kj = k;
 }
 
-struct Window { int b0, b1; bool wrapped, full; float gam; };
+struct Window { int b0, b1; bool wrapped, full; float gam, half; };
 
+// upper bound of asin(x) for 0 <= x < 1:  asin(x) <= tan(asin(x)) = x / sqrt(1 - x^2)  (a few instructions instead of asinf;
+// only used to size pruning windows, where "too large" is always safe)
+__device__ __forceinline__ float asin_ub(float x) {
+    if (!(x < 0.999f)) return 4.0f;
+    return x * rsqrtf(1.0f - x * x) * (1.0f + 4e-6f) + 2e-5f;
+}
+// bins covered by [az - half, az + half]
+__device__ __forceinline__ void set_bins(Window &w, float az, float half) {
+    w.half = half; w.wrapped = false; w.full = false; w.b0 = 0; w.b1 = VELO_AZ_BINS - 1;
+    const float lo = az - half, hi = az + half;
+    if (!(half < CUDART_PI_F)) { w.full = true; return; }
+    if (lo < -CUDART_PI_F) { w.b0 = az_bin(lo + 2.0f * CUDART_PI_F); w.b1 = az_bin(hi); w.wrapped = true; }
+    else if (hi > CUDART_PI_F) { w.b0 = az_bin(lo); w.b1 = az_bin(hi - 2.0f * CUDART_PI_F); w.wrapped = true; }
+    else { w.b0 = az_bin(lo); w.b1 = az_bin(hi); }
+    if (w.wrapped && w.b0 <= w.b1 + 1) { w.full = true; w.wrapped = false; w.b0 = 0; w.b1 = VELO_AZ_BINS - 1; }
+}
 // azimuth window / elevation tolerance for bound d2b around a query with azimuth az, xy-range D, range rho
 __device__ __forceinline__ Window make_window(float d2b, float az, float D, float rho) {
     Window w;
     const float b = sqrtf(d2b) * (1.0f + 1e-5f) + 1e-6f;
-    w.gam = (b < rho) ? asinf(b / rho) + 2e-5f : 4.0f;
-    w.full = !(b < D); w.wrapped = false; w.b0 = 0; w.b1 = VELO_AZ_BINS - 1;
-    if (!w.full) {
-        const float h = asinf(b / D) + 2e-5f;
-        float lo = az - h, hi = az + h;
-        if (h >= CUDART_PI_F) { w.full = true; }
-        else if (lo < -CUDART_PI_F) { w.b0 = az_bin(lo + 2.0f * CUDART_PI_F); w.b1 = az_bin(hi); w.wrapped = true; }
-        else if (hi > CUDART_PI_F) { w.b0 = az_bin(lo); w.b1 = az_bin(hi - 2.0f * CUDART_PI_F); w.wrapped = true; }
-        else { w.b0 = az_bin(lo); w.b1 = az_bin(hi); }
-        if (w.wrapped && w.b0 <= w.b1 + 1) { w.full = true; w.wrapped = false; w.b0 = 0; w.b1 = VELO_AZ_BINS - 1; }
-    }
+    w.gam = (b < rho) ? asin_ub(b / rho) : 4.0f;
+    set_bins(w, az, (b < D) ? asin_ub(b / D) : 4.0f);
     return w;
 }
 
 // nearest candidate of one ring inside sorted[start, end): smallest d2, ties -> lower index in ring.
 // bd starts at the smallest float above the threshold and bi at -1, so `d2 < bd` also applies the threshold (velo.h:829).
-__device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, int start, int end, float mx, float my, float mz, float &bd, int &bi) {
+__device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, int start, int end, float mx, float my, float mz, float &bd, int &bi, int &ncand) {
+    ncand += max(end - start, 0);
 #pragma unroll 4
     for (int p = start; p < end; p++) {
         const float4 c = __ldg(sorted + p);
         const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
         const int idx = __float_as_int(c.w);
-        if (d2 < bd) { bd = d2; bi = idx; }
-        else if (d2 == bd && idx < bi) bi = idx;
+        if (d2 <= bd) { if (d2 < bd || idx < bi) { bd = d2; bi = idx; } }   // rare path: taken O(log n) times per scan
     }
 }
 __device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, const int *__restrict__ cs, int s, const Window &w,
-                                         float mx, float my, float mz, float thr_excl) {
+                                         float mx, float my, float mz, float thr_excl, int &ncand) {
     float bd = thr_excl; int bi = -1;
-    if (!w.wrapped) scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi);
+    if (!w.wrapped) scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi, ncand);
     else {
-        scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), mx, my, mz, bd, bi);
-        scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi);
+        scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), mx, my, mz, bd, bi, ncand);
+        scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi, ncand);
     }
     return bi >= 0 ? make_key(bd, s, bi) : KEY_INF;
 }
-// elevation gap between el and the ring's interval over the sectors touched by the window
-__device__ __forceinline__ float ring_gap(const float2 *__restrict__ se, const Window &w, float el) {
-    float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+// Per-ring pruning from the sector boxes {elev lo, elev hi, range min, range max} of the ring inside the window's sectors.
+// With rq, rp the ranges from the index origin and `angle` the angle between the two directions,
+//     d2(q,p) = (rq - rp)^2 + 4 rq rp sin^2(angle/2),     sin^2(angle/2) = sin^2(de/2) + cos(eq) cos(ep) sin^2(daz/2)   (haversine)
+// so (a) d2 >= dr^2 + 4 rq rlo sin^2(gap/2) =: lb2 (ring skipped when lb2 > bound) and (b) a point within the bound has
+//     sin^2(daz/2) <= (bound - dr^2) / (4 rq rlo cos(eq) cos(ep))   -> a narrower azimuth window for this ring.
+// Every quantity is deflated/inflated so that float error in this pruning math can only keep extra candidates.
+__device__ __forceinline__ bool ring_test(const float4 *__restrict__ sb4, const Window &w, float az, float el, float rho, float bnd, Window &wr) {
+    float elo = CUDART_INF_F, ehi = -CUDART_INF_F, rlo = CUDART_INF_F, rhi = -CUDART_INF_F;
     int sa = w.b0 / VELO_BINS_PER_SECTOR, sb = w.b1 / VELO_BINS_PER_SECTOR;
     if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
     for (int sec = sa;; sec = (sec + 1) & (VELO_SECTORS - 1)) {
-        const float2 e = __ldg(se + sec);
-        lo = fminf(lo, e.x); hi = fmaxf(hi, e.y);
+        const float4 e = __ldg(sb4 + sec);
+        elo = fminf(elo, e.x); ehi = fmaxf(ehi, e.y); rlo = fminf(rlo, e.z); rhi = fmaxf(rhi, e.w);
         if (sec == sb) break;
     }
-    return fmaxf(fmaxf(lo - el, el - hi), 0.0f);   // +inf when the sectors are empty
+    if (!(elo <= ehi)) return false;                                // no point of the ring in these sectors
+    const float g = fmaxf(fmaxf(elo - el, el - ehi) - 2e-5f, 0.0f);
+    const float dr = fmaxf(fmaxf(rlo - rho, rho - rhi) - 1e-5f * (rho + rhi) - 1e-6f, 0.0f);
+    const float h = fminf(0.5f * g, 1.0f);
+    const float sh = h * (1.0f - h * h * (1.0f / 6.0f));           // <= sin(h) for 0 <= h <= 1
+    const float rr = 4.0f * rho * fmaxf(rlo, 0.0f) * (1.0f - 1e-5f);
+    const float dr2 = dr * dr * (1.0f - 1e-5f);
+    if ((dr2 + rr * sh * sh) * (1.0f - 1e-4f) > bnd) return false;
+    wr = w;
+    const float em = fmaxf(fabsf(elo), fabsf(ehi));
+    const float cc = (1.0f - 0.5f * el * el) * (1.0f - 0.5f * em * em) * (1.0f - 1e-5f);   // <= cos(eq) cos(ep)
+    if (cc > 0.1f && rr > 1e-3f) {
+        const float rem = bnd * (1.0f + 2e-5f) + 1e-7f - dr2;
+        const float s2 = fmaxf(rem, 0.0f) / (rr * cc);
+        if (s2 < 0.8f) {
+            const float half = 2.0f * asin_ub(sqrtf(s2) * (1.0f + 1e-5f)) + 2e-5f;
+            if (half < w.half) set_bins(wr, az, half);
+        }
+    }
+    return true;
 }
 // candidate rings (64-ring word `word`) whose elevation interval in a sector of the window can come within w.gam of el
 __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 *__restrict__ mhi, int W, int word, const Window &w, float el) {
@@ -107,11 +138,12 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     __shared__ double s_rows[ICP_THREADS / 32][32 * NEQ_ROW];
     __shared__ double s_red[(ICP_THREADS / 32) * 56];
     __shared__ int s_kept;
+    __shared__ unsigned long long s_stat[4];
     __shared__ PosePack s_P;
     const IcpUnit &U = units[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (U.src_slot < 0) {   // unit without a previous scan: contributes nothing
-        if (tid < 59) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + tid] = 0.0;
+        if (tid < 64) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + tid] = 0.0;
         return;
     }
     const int nrM = B.n_rings[U.src_slot], nrS = B.n_rings[U.tgt_slot];
@@ -121,7 +153,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     for (int i = tid; i < (int)(sizeof(PosePack) / sizeof(double)); i += blockDim.x)
         reinterpret_cast<double *>(&s_P)[i] = reinterpret_cast<const double *>(&U.pose)[i];
     if (tid == 0) {
-        int q = 0; s_kept = 0;
+        int q = 0; s_kept = 0; s_stat[0] = s_stat[1] = s_stat[2] = s_stat[3] = 0ull;
         for (int s = 0; s < nrM; s++) { s_q[s] = q; int r0 = rsM[s], L = rsM[s + 1] - r0; s_rsM[s] = r0; q += (L + skip - 1) / skip; }
         s_q[nrM] = q;
     }
@@ -133,19 +165,22 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
     const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
-    const float2 *seS = B.sec_elev + (size_t)U.tgt_slot * B.R * VELO_SECTORS;
+    const float4 *sbS = B.sec_box + (size_t)U.tgt_slot * B.R * VELO_SECTORS;
     const int W = B.W;
     const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const PosePack &P = s_P;
     const float thr_f = U.thr_f, thr_excl = U.thr_excl;
     double acc = 0.0, raw = 0.0;
-    int kept_local = 0;
+    int kept_local = 0, st_seed = 0, st_exh = 0, st_rings = 0, st_mask = 0;   // search statistics -> neq[59..62]
 
     for (int qb = q0; qb < q1; qb += ICP_THREADS) {
         const int q = qb + tid;
         bool kept = false;
         double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
+#ifdef VELO_ICP_DEBUG
+        const int dbg0 = st_seed, dbg1 = st_exh, dbg2 = st_rings, dbg3 = st_mask;
+#endif
         if (q < q1) {
             // (sm, smi) of this query: velo.h:806-807
             int lo = 0, hi = nrM - 1;
@@ -180,38 +215,62 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
             const int bq = az_bin(az);
 
             u64 ki = KEY_INF, kj = KEY_INF;
-            // seeds: up to 3 rings whose elevation interval is within SEED_GAM of the query, +-1 azimuth bin each
-            // -> a tight bound before the exhaustive pass (any real point gives a valid bound)
+            const float gam_thr = make_window(thr_f, az, D, rho).gam;      // elevation tolerance of the distance threshold itself
+            // Phase 1 (probe): rings in order of increasing elevation gap (levels of doubling tolerance, read from the ring
+            // masks), only the query's own azimuth bin of each, until two rings hold a candidate.  Any real point is a valid
+            // bound, so this only serves to start the exhaustive phase with a small search radius.
             {
-                Window ws; ws.full = false; ws.wrapped = false; ws.gam = 0.0065f;
-                ws.b0 = max(bq - 1, 0); ws.b1 = min(bq + 1, VELO_AZ_BINS - 1);
-                int seeds = 0;
-                for (int word = 0; word < W && seeds < 3; word++) {
-                    u64 m = ring_mask(mloS, mhiS, W, word, ws, el);
-                    while (m && seeds < 3) {
-                        const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; seeds++;
-                        merge_key(scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, ws, mx, my, mz, thr_excl), ki, kj);
+                Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq;
+                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
+                for (float lev = 0.0065f; kj == KEY_INF; lev *= 2.0f) {
+                    ws.gam = fminf(lev, gam_thr);
+#pragma unroll
+                    for (int word = 0; word < 4; word++) {
+                        if (word >= W) break;
+                        u64 m = ring_mask(mloS, mhiS, W, word, ws, el) & ~V[word];
+                        V[word] |= m;
+                        while (m && kj == KEY_INF) {
+                            const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1;
+                            merge_key(scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, ws, mx, my, mz, thr_excl, st_seed), ki, kj);
+                        }
                     }
+                    if (!(lev < gam_thr)) break;
                 }
             }
-            // exhaustive pass, pruned by the current bound on d2_j (velo.h:825-848): only rings in the mask can hold a
-            // point within the bound; each is visited once (the mask only shrinks when the bound does)
+            // Phase 2 (exhaustive): every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is
+            // visited exactly once, again nearest elevation first; the bound, the azimuth window and the elevation tolerance
+            // shrink whenever the runner-up improves.
             float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+#ifdef VELO_ICP_DEBUG
+            const float dbg_si = (ki == KEY_INF) ? -1.f : sqrtf(key_d2(ki)), dbg_sj = (kj == KEY_INF) ? -1.f : sqrtf(key_d2(kj));
+#endif
             Window w = make_window(bound, az, D, rho);
-            for (int word = 0; word < W; word++) {
-                u64 m = ring_mask(mloS, mhiS, W, word, w, el), done = 0ull;
-                while (m) {
-                    const int bit = __ffsll((long long)m) - 1; m &= m - 1; done |= 1ull << bit;
-                    const int s = word * 64 + bit;
-                    if (ring_gap(seS + s * VELO_SECTORS, w, el) > w.gam) continue;
-                    const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, w, mx, my, mz, thr_excl);
-                    if (k == KEY_INF) continue;
-                    const u64 oj = kj;
-                    merge_key(k, ki, kj);
-                    if (kj != oj) {
-                        bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho);
-                        m = ring_mask(mloS, mhiS, W, word, w, el) & ~done;
+            {
+                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
+                for (float lev = 0.0065f;; lev *= 2.0f) {
+                    const float gcur = fminf(lev, w.gam);
+                    Window wl = w; wl.gam = gcur;
+#pragma unroll
+                    for (int word = 0; word < 4; word++) {
+                        if (word >= W) break;
+                        u64 m = ring_mask(mloS, mhiS, W, word, wl, el) & ~V[word];
+                        V[word] |= m;
+                        while (m) {
+                            const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
+                            // a ring that already holds the best candidate only needs points that beat its own candidate
+                            const bool own = (ki != KEY_INF) && (s == key_ring(ki));
+                            const float bnd_s = own ? key_d2(ki) : bound;
+                            Window wr;
+                            if (!ring_test(sbS + s * VELO_SECTORS, w, az, el, rho, bnd_s, wr)) continue;
+                            const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, wr, mx, my, mz, thr_excl, st_exh);
+                            st_rings++;
+                            if (k == KEY_INF) continue;
+                            const u64 oj = kj;
+                            merge_key(k, ki, kj);
+                            if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+                        }
                     }
+                    if (!(gcur < w.gam)) break;      // all rings within the (possibly reduced) tolerance have been visited
                 }
             }
 
@@ -263,6 +322,10 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
             if (corr) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
+#ifdef VELO_ICP_DEBUG   /* tools/icp_stats.py --debug: per-query search statistics instead of the translation Jacobian */
+                rec.jacobian[0] = dbg_si; rec.jacobian[1] = dbg_sj; rec.jacobian[2] = (kj == KEY_INF) ? -1.0 : sqrt((double)key_d2(kj));
+                rec.jacobian[3] = st_seed - dbg0; rec.jacobian[4] = st_exh - dbg1; rec.jacobian[5] = (st_rings - dbg2) + 1000.0 * (st_mask - dbg3);
+#endif
                 corr[q] = rec;
             }
         }
@@ -272,9 +335,17 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     // reduce
     for (int o = 16; o > 0; o >>= 1) kept_local += __shfl_down_sync(FULL, kept_local, o);
     if (lane == 0 && kept_local) atomicAdd(&s_kept, kept_local);
+    for (int o = 16; o > 0; o >>= 1) {
+        st_seed += __shfl_down_sync(FULL, st_seed, o); st_exh += __shfl_down_sync(FULL, st_exh, o);
+        st_rings += __shfl_down_sync(FULL, st_rings, o); st_mask += __shfl_down_sync(FULL, st_mask, o);
+    }
+    if (lane == 0) { atomicAdd(&s_stat[0], (u64)st_seed); atomicAdd(&s_stat[1], (u64)st_exh); atomicAdd(&s_stat[2], (u64)st_rings); atomicAdd(&s_stat[3], (u64)st_mask); }
     double *pout = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64;
     block_neq_finish(s_red, acc, raw, pout);
-    if (tid == 0) { pout[56] = (double)s_kept; pout[57] = (double)s_kept; pout[58] = (double)(q1 > q0 ? q1 - q0 : 0); }
+    if (tid == 0) {
+        pout[56] = (double)s_kept; pout[57] = (double)s_kept; pout[58] = (double)(q1 > q0 ? q1 - q0 : 0);
+        for (int i = 0; i < 4; i++) pout[59 + i] = (double)s_stat[i];
+    }
 }
 
 // fixed-order sum of the per-CTA partials of one unit: out[u][0..58]
@@ -282,7 +353,7 @@ __global__ void k_neq_reduce(const double *__restrict__ partial, double *__restr
     const int u = blockIdx.x, t = threadIdx.x;
     if (t >= VELO_NEQ_STRIDE) return;
     double s = 0.0;
-    if (t < 59) for (int c = 0; c < ctas; c++) s += partial[((size_t)u * ctas + c) * 64 + t];
+    if (t < 63) for (int c = 0; c < ctas; c++) s += partial[((size_t)u * ctas + c) * 64 + t];
     out[(size_t)u * VELO_NEQ_STRIDE + t] = s;
 }
 

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_ingest_permute(DevBuffers B, DevCalib c
 __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal, int slot0) {
     __shared__ int s_hist[VELO_AZ_BINS];
     __shared__ int s_cur[VELO_AZ_BINS];
-    __shared__ int s_lo[VELO_SECTORS], s_hi[VELO_SECTORS];
+    __shared__ int s_lo[VELO_SECTORS], s_hi[VELO_SECTORS], s_rlo[VELO_SECTORS], s_rhi[VELO_SECTORS];
     __shared__ int s_w[33];
     const int slot = slot0 + blockIdx.y, ring = blockIdx.x, tid = threadIdx.x;
     if (ring >= B.n_rings[slot]) return;
@@ -98,16 +98,19 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
     const int r0 = rs[ring], L = rs[ring + 1] - r0;
     const float4 *pts = B.pts + (size_t)slot * B.N + r0;
     for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) { s_hist[i] = 0; s_cur[i] = 0; }
-    if (tid < VELO_SECTORS) { s_lo[tid] = f2ord(CUDART_INF_F); s_hi[tid] = f2ord(-CUDART_INF_F); }
+    if (tid < VELO_SECTORS) { s_lo[tid] = s_rlo[tid] = f2ord(CUDART_INF_F); s_hi[tid] = s_rhi[tid] = f2ord(-CUDART_INF_F); }
     __syncthreads();
     for (int i = tid; i < L; i += blockDim.x) {
         float4 p = pts[i];
         float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
         int b = az_bin(atan2f(vy, vx));
-        int e = f2ord(atan2f(vz, sqrtf(vx * vx + vy * vy)));
+        const float dxy2 = vx * vx + vy * vy;
+        int e = f2ord(atan2f(vz, sqrtf(dxy2))), rr = f2ord(sqrtf(dxy2 + vz * vz));
         atomicAdd(&s_hist[b], 1);
         atomicMin(&s_lo[b / VELO_BINS_PER_SECTOR], e);
         atomicMax(&s_hi[b / VELO_BINS_PER_SECTOR], e);
+        atomicMin(&s_rlo[b / VELO_BINS_PER_SECTOR], rr);
+        atomicMax(&s_rhi[b / VELO_BINS_PER_SECTOR], rr);
     }
     __syncthreads();
     // exclusive scan of 512 bins with 256 threads (2 bins each)
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
     for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) cs[i] = r0 + s_hist[i];
     if (tid == 0) cs[VELO_AZ_BINS] = r0 + L;
     if (tid < VELO_SECTORS)
-        B.sec_elev[((size_t)slot * B.R + ring) * VELO_SECTORS + tid] = make_float2(ord2f(s_lo[tid]), ord2f(s_hi[tid]));
+        B.sec_box[((size_t)slot * B.R + ring) * VELO_SECTORS + tid] = make_float4(ord2f(s_lo[tid]), ord2f(s_hi[tid]), ord2f(s_rlo[tid]), ord2f(s_rhi[tid]));
     float4 *sorted = B.sorted + (size_t)slot * B.N + r0;
     for (int i = tid; i < L; i += blockDim.x) {
         float4 p = pts[i];
@@ -137,14 +140,14 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
 __global__ void __launch_bounds__(VELO_EL_BUCKETS) k_index_masks(DevBuffers B, int slot0) {
     const int slot = slot0 + blockIdx.y, sec = blockIdx.x, b = threadIdx.x;
     const int nr = B.n_rings[slot];
-    const float2 *se = B.sec_elev + (size_t)slot * B.R * VELO_SECTORS + sec;
+    const float4 *se = B.sec_box + (size_t)slot * B.R * VELO_SECTORS + sec;
     unsigned long long *mlo = B.mask_lo + (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
     unsigned long long *mhi = B.mask_hi + (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
     for (int w = 0; w < B.W; w++) {
         unsigned long long lo = 0ull, hi = 0ull;
         const int r1 = min(nr, (w + 1) * 64);
         for (int r = w * 64; r < r1; r++) {
-            const float2 e = se[(size_t)r * VELO_SECTORS];
+            const float4 e = se[(size_t)r * VELO_SECTORS];
             if (e.x <= e.y) {                                   // sector not empty for this ring
                 if (el_bucket(e.x) <= b) lo |= 1ull << (r & 63);
                 if (el_bucket(e.y) >= b) hi |= 1ull << (r & 63);

@@ -233,6 +233,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roof,
         "kernels": kernels,
         "gen_seconds": round(t_gen, 2),
+        "icp_search": {"per_pass_candidates_per_query": [round(float((icp[1:, p, 59].sum() + icp[1:, p, 60].sum()) / max(icp[1:, p, 58].sum(), 1)), 1) for p in range(batch.n_passes)],
+                       "per_pass_rings_scanned_per_query": [round(float(icp[1:, p, 61].sum() / max(icp[1:, p, 58].sum(), 1)), 2) for p in range(batch.n_passes)],
+                       "per_pass_kept_frac": [round(float(icp[1:, p, 56].sum() / max(icp[1:, p, 58].sum(), 1)), 3) for p in range(batch.n_passes)]},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, prm, cal, synth)

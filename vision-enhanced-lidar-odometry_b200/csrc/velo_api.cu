@@ -237,12 +237,13 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &B.matches, S * C * MM * 2)); CKC(dalloc(ctx, &B.n_matches, S * C));
     // units / normal equations
     ctx->icp_partial_ctas = 296;
-    const size_t n_icp_units = S * P, n_vis_units = S * (size_t)(prm->f2f_iterations > 0 ? prm->f2f_iterations : 1);
+    if (prm->max_icp_passes > VELO_MAX_PASSES) { velo_gpu_destroy(ctx); return fail(nullptr, VELO_ERR_INVALID_ARG, "max_icp_passes exceeds VELO_MAX_PASSES (8)"); }
+    const size_t n_icp_units = S, n_vis_units = S * (size_t)(prm->f2f_iterations > 0 ? prm->f2f_iterations : 1);
     CKC(cudaMallocHost((void **)&ctx->h_icp_units, n_icp_units * sizeof(IcpUnit)));
     CKC(cudaMallocHost((void **)&ctx->h_vis_units, n_vis_units * sizeof(VisUnit)));
     CKC(dalloc(ctx, &ctx->d_icp_units, n_icp_units)); CKC(dalloc(ctx, &ctx->d_vis_units, n_vis_units));
-    size_t part = n_icp_units * 8; if (part < (size_t)ctx->icp_partial_ctas) part = ctx->icp_partial_ctas;
-    CKC(dalloc(ctx, &ctx->d_icp_partial, part * 64)); CKC(dalloc(ctx, &ctx->d_icp_out, n_icp_units * VELO_NEQ_STRIDE));
+    size_t part = n_icp_units * 32; if (part < (size_t)ctx->icp_partial_ctas) part = ctx->icp_partial_ctas;
+    CKC(dalloc(ctx, &ctx->d_icp_partial, part * VELO_MAX_PASSES * 64)); CKC(dalloc(ctx, &ctx->d_icp_out, S * P * VELO_NEQ_STRIDE));
     ctx->vis_ctas = 0;
     size_t vpart = n_vis_units * 4; if (vpart < 64) vpart = 64;
     CKC(dalloc(ctx, &ctx->d_vis_partial, vpart * 64)); CKC(dalloc(ctx, &ctx->d_vis_out, n_vis_units * VELO_NEQ_STRIDE));
@@ -479,19 +480,23 @@ extern "C" int velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int se
     return VELO_OK;
 }
 
-static void fill_icp_unit(const velo_gpu_ctx *ctx, IcpUnit *u, int src, int tgt, const double pose[6], int iter, int skip) {
+static void init_icp_unit(const velo_gpu_ctx *ctx, IcpUnit *u, int src, int tgt, int skip) {
     memset(u, 0, sizeof(*u));
-    u->src_slot = src; u->tgt_slot = tgt; u->iter = iter; u->skip = skip;
-    const double thr = ctx->prm.correspondence_thresh_icp / iter / iter / iter / iter;     // velo.h:829
-    u->thr_f = floor_to_float(thr);
-    u->thr_excl = nextafterf(u->thr_f, INFINITY);
+    u->src_slot = src; u->tgt_slot = tgt; u->skip = skip; u->n_pass = 0;
     u->norm_thr_f = ceil_to_float(ctx->prm.icp_norm_condition);                            // velo.h:873
     u->loss_a = ctx->prm.loss_thresh_3DPD; u->weight = ctx->prm.weight_3DPD;               // velo.h:885-891
-    make_pose_pack(pose, &u->pose);
+}
+static void add_icp_pass(const velo_gpu_ctx *ctx, IcpUnit *u, const double pose[6], int iter) {
+    IcpPass *p = &u->pass[u->n_pass++];
+    const double thr = ctx->prm.correspondence_thresh_icp / iter / iter / iter / iter;     // velo.h:829
+    p->thr_f = floor_to_float(thr);
+    p->thr_excl = nextafterf(p->thr_f, INFINITY);
+    p->iter = iter;
+    make_pose_pack(pose, &p->pose);
 }
 static int auto_ctas(const velo_gpu_ctx *ctx, int n_units, int cap) {
     int c = ctx->prm.ctas_per_icp_unit;
-    if (c <= 0) { c = (148 * 12 + n_units - 1) / n_units; if (c < 8) c = 8; }
+    if (c <= 0) { c = (148 * 6 * 10 + n_units - 1) / n_units; if (c < 8) c = 8; }   // ~10 waves of 6 CTAs/SM
     if (c > cap) c = cap;
     return c < 1 ? 1 : c;
 }
@@ -504,11 +509,12 @@ extern "C" int velo_gpu_icp_pass(velo_gpu_ctx *ctx, int slot_M, int slot_S, cons
     CK(cudaSetDevice(ctx->device));
     int st = slot_status(ctx, slot_M); if (st) return st;
     st = slot_status(ctx, slot_S); if (st) return st;
-    fill_icp_unit(ctx, &ctx->h_icp_units[0], slot_M, slot_S, pose, iter, icp_skip);
+    init_icp_unit(ctx, &ctx->h_icp_units[0], slot_M, slot_S, icp_skip);
+    add_icp_pass(ctx, &ctx->h_icp_units[0], pose, iter);
     CK(cudaMemcpyAsync(ctx->d_icp_units, ctx->h_icp_units, sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
     const int ctas = auto_ctas(ctx, 1, ctx->icp_partial_ctas);
     if (corr) CK(cudaMemsetAsync(ctx->d_corr, 0, (size_t)ctx->B.N * sizeof(velo_icp_corr), ctx->stream));
-    launch_icp(launcher(ctx), ctx->B, ctx->dcal, ctx->d_icp_units, 1, ctas, ctx->d_icp_partial, ctx->d_icp_out, corr ? ctx->d_corr : nullptr);
+    launch_icp(launcher(ctx), ctx->B, ctx->dcal, ctx->d_icp_units, 1, 1, ctas, ctx->d_icp_partial, ctx->d_icp_out, 1, corr ? ctx->d_corr : nullptr);
     CK(cudaGetLastError());
     double out[VELO_NEQ_STRIDE];
     CK(cudaMemcpyAsync(out, ctx->d_icp_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
@@ -617,14 +623,14 @@ extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, co
     if (in->icp_poses && in->pass_iter) {
         if (in->n_passes < 1 || in->n_passes > B.P) return fail(ctx, VELO_ERR_CAPACITY, "n_passes exceeds max_icp_passes");
         ctx->batch_passes = in->n_passes;
-        for (int i = 0; i < count; i++) for (int p = 0; p < in->n_passes; p++) {
+        for (int p = 0; p < in->n_passes; p++) if (in->pass_iter[p] < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "pass_iter must be >= 1");
+        for (int i = 0; i < count; i++) {
             const int slot = slot0 + i;
-            IcpUnit *u = &ctx->h_icp_units[(size_t)slot * B.P + p];
-            if (in->pass_iter[p] < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "pass_iter must be >= 1");
-            fill_icp_unit(ctx, u, slot, slot - 1, in->icp_poses + 6 * ((size_t)i * in->n_passes + p), in->pass_iter[p], ctx->prm.icp_skip);
-            if (slot == 0) u->src_slot = -1;
+            IcpUnit *u = &ctx->h_icp_units[slot];
+            init_icp_unit(ctx, u, slot == 0 ? -1 : slot, slot - 1, ctx->prm.icp_skip);
+            for (int p = 0; p < in->n_passes; p++) add_icp_pass(ctx, u, in->icp_poses + 6 * ((size_t)i * in->n_passes + p), in->pass_iter[p]);
         }
-        CK(cudaMemcpyAsync(ctx->d_icp_units + (size_t)slot0 * B.P, ctx->h_icp_units + (size_t)slot0 * B.P, (size_t)count * B.P * sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_icp_units + slot0, ctx->h_icp_units + slot0, (size_t)count * sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (in->vis_poses) {
         const int V = ctx->prm.f2f_iterations;
@@ -656,12 +662,11 @@ extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int s
     const int skip_first = (first_has_prev && slot0 > 0) ? 0 : 1;
     const int pairs = count - skip_first, s_first = slot0 + skip_first;
     if ((stages & VELO_STAGE_ICP) && pairs > 0 && ctx->batch_passes > 0) {
-        if (ctx->batch_passes != B.P) return fail(ctx, VELO_ERR_STATE, "batched ICP needs n_passes == max_icp_passes (dense unit layout)");
-        const int n_units = pairs * B.P;
-        const int ctas = auto_ctas(ctx, n_units, 8);
+        const int n_units = pairs;
+        const int ctas = auto_ctas(ctx, n_units, 32);
         if (skip_first) CK(cudaMemsetAsync(ctx->d_icp_out + (size_t)slot0 * B.P * VELO_NEQ_STRIDE, 0, (size_t)B.P * VELO_NEQ_STRIDE * sizeof(double), ctx->stream));
-        launch_icp(L, B, ctx->dcal, ctx->d_icp_units + (size_t)s_first * B.P, n_units, ctas, ctx->d_icp_partial,
-                   ctx->d_icp_out + (size_t)s_first * B.P * VELO_NEQ_STRIDE, nullptr);
+        launch_icp(L, B, ctx->dcal, ctx->d_icp_units + s_first, n_units, ctx->batch_passes, ctas, ctx->d_icp_partial,
+                   ctx->d_icp_out + (size_t)s_first * B.P * VELO_NEQ_STRIDE, B.P, nullptr);
     }
     if ((stages & VELO_STAGE_VISUAL) && pairs > 0 && ctx->batch_vis > 0) {
         const int V = ctx->prm.f2f_iterations;

@@ -66,15 +66,23 @@ struct PosePack {
     int pad;
 };
 
+#define VELO_MAX_PASSES 8        /* ICP passes per frame pair in one launch (f2f_iterations * icp_iterations = 6) */
+
+struct IcpPass {
+    PosePack pose;
+    float thr_f;              // largest float f with (double)f <= correspondence_thresh_icp/iter^4 (velo.h:829)
+    float thr_excl;           // smallest float above thr_f (exclusive bound of the candidate loop)
+    int iter, pad;
+};
+
+// one frame pair (source = current scan, target = previous scan) with its supplied poses
 struct IcpUnit {
     int src_slot, tgt_slot;
-    int iter, skip;
-    float thr_f;              // largest float f with (double)f <= correspondence_thresh_icp/iter^4 (velo.h:829)
-    float norm_thr_f;         // smallest float f with (double)f >= icp_norm_condition (velo.h:873)
-    float thr_excl, pad0;     // smallest float above thr_f (exclusive bound of the candidate loop)
+    int skip, n_pass;
+    float norm_thr_f, pad0;   // smallest float f with (double)f >= icp_norm_condition (velo.h:873)
     double loss_a;            // loss_thresh_3DPD
     double weight;            // weight_3DPD
-    PosePack pose;
+    IcpPass pass[VELO_MAX_PASSES];
 };
 
 struct VisUnit {
@@ -103,8 +111,9 @@ void launch_ingest(const Launcher &L, const DevBuffers &B, const DevCalib &cal, 
 void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
 void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams);
-// units: device array [n_units]; partial: [n_units][ctas][64] doubles; out: [n_units][VELO_NEQ_STRIDE]; corr optional (single unit)
-void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int ctas,
-                double *partial, double *out, velo_icp_corr *corr);
+// units: device array [n_units]; partial: [n_units][ctas][VELO_MAX_PASSES][64] doubles; out: [n_units][out_stride_passes][VELO_NEQ_STRIDE];
+// corr optional (single unit, records of its last pass)
+void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
+                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr);
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
                    const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas);

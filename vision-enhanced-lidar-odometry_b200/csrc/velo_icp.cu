@@ -12,7 +12,7 @@
 // only inside the azimuth window asin(b/|q_xy|), b = current bound on sqrt(d2_j).
 #include "velo_common.cuh"
 
-#define ICP_THREADS 256
+#define ICP_THREADS 128
 #define KEY_INF 0xFFFFFFFFFFFFFFFFull
 
 __device__ __forceinline__ u64 make_key(float d2, int ring, int idx) {
@@ -124,36 +124,41 @@ __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 
     if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
     u64 m = 0ull;
     for (int sec = sa;; sec = (sec + 1) & (VELO_SECTORS - 1)) {
-        m |= __ldg(mlo + ((size_t)sec * VELO_EL_BUCKETS + e1) * W + word) & __ldg(mhi + ((size_t)sec * VELO_EL_BUCKETS + e0) * W + word);
+        m |= __ldg(mlo + (sec * VELO_EL_BUCKETS + e1) * W + word) & __ldg(mhi + (sec * VELO_EL_BUCKETS + e0) * W + word);
         if (sec == sb) break;
     }
     return m;
 }
 
-// grid = (ctas per unit, n_units); one thread = one query at a time
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
+// grid = (ctas per unit, n_units).  A unit is one frame pair with up to VELO_MAX_PASSES supplied poses (the ICP passes of
+// frameToFrame, velo.h:616,800).  One thread = one query point at a time, looping over the passes: the correspondence of
+// pass p (two real target points) seeds pass p+1 with an immediately tight bound, so only the first pass needs the probe.
+__global__ void __launch_bounds__(ICP_THREADS, 6) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
                                                           double *__restrict__ partial, velo_icp_corr *__restrict__ corr) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
     __shared__ double s_rows[ICP_THREADS / 32][32 * NEQ_ROW];
-    __shared__ double s_red[(ICP_THREADS / 32) * 56];
-    __shared__ int s_kept;
-    __shared__ unsigned long long s_stat[4];
-    __shared__ PosePack s_P;
+    __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];
+    __shared__ unsigned long long s_stat[VELO_MAX_PASSES][5];
+    __shared__ IcpPass s_pass[VELO_MAX_PASSES];
     const IcpUnit &U = units[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int NP = U.n_pass;
+    double *pbase = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * VELO_MAX_PASSES * 64;
     if (U.src_slot < 0) {   // unit without a previous scan: contributes nothing
-        if (tid < 64) partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + tid] = 0.0;
+        for (int i = tid; i < VELO_MAX_PASSES * 64; i += blockDim.x) pbase[i] = 0.0;
         return;
     }
-    const int nrM = B.n_rings[U.src_slot], nrS = B.n_rings[U.tgt_slot];
+    const int nrM = B.n_rings[U.src_slot];
     const int *rsM = B.ring_start + (size_t)U.src_slot * (B.R + 1);
     const int *rsS = B.ring_start + (size_t)U.tgt_slot * (B.R + 1);
     const int skip = U.skip;
-    for (int i = tid; i < (int)(sizeof(PosePack) / sizeof(double)); i += blockDim.x)
-        reinterpret_cast<double *>(&s_P)[i] = reinterpret_cast<const double *>(&U.pose)[i];
+    for (int i = tid; i < (int)(NP * sizeof(IcpPass) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(s_pass)[i] = reinterpret_cast<const double *>(U.pass)[i];
+    for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 56; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
+    for (int i = tid; i < VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0])[i] = 0ull;
     if (tid == 0) {
-        int q = 0; s_kept = 0; s_stat[0] = s_stat[1] = s_stat[2] = s_stat[3] = 0ull;
+        int q = 0;
         for (int s = 0; s < nrM; s++) { s_q[s] = q; int r0 = rsM[s], L = rsM[s + 1] - r0; s_rsM[s] = r0; q += (L + skip - 1) / skip; }
         s_q[nrM] = q;
     }
@@ -169,202 +174,227 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_pass(DevBuffers B, DevCalib
     const int W = B.W;
     const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
-    const PosePack &P = s_P;
-    const float thr_f = U.thr_f, thr_excl = U.thr_excl;
-    double acc = 0.0, raw = 0.0;
-    int kept_local = 0, st_seed = 0, st_exh = 0, st_rings = 0, st_mask = 0;   // search statistics -> neq[59..62]
 
     for (int qb = q0; qb < q1; qb += ICP_THREADS) {
         const int q = qb + tid;
-        bool kept = false;
-        double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
-#ifdef VELO_ICP_DEBUG
-        const int dbg0 = st_seed, dbg1 = st_exh, dbg2 = st_rings, dbg3 = st_mask;
-#endif
-        if (q < q1) {
-            // (sm, smi) of this query: velo.h:806-807
+        const bool active = q < q1;
+        int sm = 0, smi = 0;
+        float4 pm = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {                                   // (sm, smi) of this query: velo.h:806-807
             int lo = 0, hi = nrM - 1;
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_q[mid] <= q) lo = mid; else hi = mid - 1; }
-            const int sm = lo, smi = (q - s_q[sm]) * skip;
-            const float4 pm = __ldg(ptsM + s_rsM[sm] + smi);
-            // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
-            const double x0 = pm.x, x1 = pm.y, x2 = pm.z;
-            double y0, y1, y2;
-            if (!P.small_angle) {
-                const double c0 = __dsub_rn(__dmul_rn(P.u[1], x2), __dmul_rn(P.u[2], x1));
-                const double c1 = __dsub_rn(__dmul_rn(P.u[2], x0), __dmul_rn(P.u[0], x2));
-                const double c2 = __dsub_rn(__dmul_rn(P.u[0], x1), __dmul_rn(P.u[1], x0));
-                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.u[0], x0), __dmul_rn(P.u[1], x1)), __dmul_rn(P.u[2], x2));
-                const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.c));
-                y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.c), __dmul_rn(c0, P.s)), __dmul_rn(P.u[0], tmp));
-                y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.c), __dmul_rn(c1, P.s)), __dmul_rn(P.u[1], tmp));
-                y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.c), __dmul_rn(c2, P.s)), __dmul_rn(P.u[2], tmp));
-            } else {
-                y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.w[1], x2), __dmul_rn(P.w[2], x1)));
-                y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.w[2], x0), __dmul_rn(P.w[0], x2)));
-                y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.w[0], x1), __dmul_rn(P.w[1], x0)));
-            }
-            const float mx = __double2float_rn(__dadd_rn(y0, P.t[0]));
-            const float my = __double2float_rn(__dadd_rn(y1, P.t[1]));
-            const float mz = __double2float_rn(__dadd_rn(y2, P.t[2]));
+            sm = lo; smi = (q - s_q[sm]) * skip;
+            pm = __ldg(ptsM + s_rsM[sm] + smi);
+        }
+        const double x0 = pm.x, x1 = pm.y, x2 = pm.z;
+        u64 pki = KEY_INF, pkj = KEY_INF;               // correspondence of the previous pass (ring / index parts are the seeds)
 
-            // ---- pruning geometry of the query in the index frame of the target scan
-            float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
-            const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
-            const float az = atan2f(vy, vx), el = atan2f(vz, D);
-            const int bq = az_bin(az);
+        for (int ps = 0; ps < NP; ps++) {
+            const IcpPass &P = s_pass[ps];
+            const float thr_f = P.thr_f, thr_excl = P.thr_excl;
+            bool kept = false;
+            double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
+            int st_seed = 0, st_exh = 0, st_rings = 0, st_mask = 0;
+            if (active) {
+                // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
+                double y0, y1, y2;
+                if (!P.pose.small_angle) {
+                    const double c0 = __dsub_rn(__dmul_rn(P.pose.u[1], x2), __dmul_rn(P.pose.u[2], x1));
+                    const double c1 = __dsub_rn(__dmul_rn(P.pose.u[2], x0), __dmul_rn(P.pose.u[0], x2));
+                    const double c2 = __dsub_rn(__dmul_rn(P.pose.u[0], x1), __dmul_rn(P.pose.u[1], x0));
+                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.pose.u[0], x0), __dmul_rn(P.pose.u[1], x1)), __dmul_rn(P.pose.u[2], x2));
+                    const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.pose.c));
+                    y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.pose.c), __dmul_rn(c0, P.pose.s)), __dmul_rn(P.pose.u[0], tmp));
+                    y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.pose.c), __dmul_rn(c1, P.pose.s)), __dmul_rn(P.pose.u[1], tmp));
+                    y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.pose.c), __dmul_rn(c2, P.pose.s)), __dmul_rn(P.pose.u[2], tmp));
+                } else {
+                    y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.pose.w[1], x2), __dmul_rn(P.pose.w[2], x1)));
+                    y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.pose.w[2], x0), __dmul_rn(P.pose.w[0], x2)));
+                    y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.pose.w[0], x1), __dmul_rn(P.pose.w[1], x0)));
+                }
+                const float mx = __double2float_rn(__dadd_rn(y0, P.pose.t[0]));
+                const float my = __double2float_rn(__dadd_rn(y1, P.pose.t[1]));
+                const float mz = __double2float_rn(__dadd_rn(y2, P.pose.t[2]));
 
-            u64 ki = KEY_INF, kj = KEY_INF;
-            const float gam_thr = make_window(thr_f, az, D, rho).gam;      // elevation tolerance of the distance threshold itself
-            // Phase 1 (probe): rings in order of increasing elevation gap (levels of doubling tolerance, read from the ring
-            // masks), only the query's own azimuth bin of each, until two rings hold a candidate.  Any real point is a valid
-            // bound, so this only serves to start the exhaustive phase with a small search radius.
-            {
-                Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq;
-                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                for (float lev = 0.0065f; kj == KEY_INF; lev *= 2.0f) {
-                    ws.gam = fminf(lev, gam_thr);
+                // ---- pruning geometry of the query in the index frame of the target scan
+                float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
+                const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
+                const float az = atan2f(vy, vx), el = atan2f(vz, D);
+                const int bq = az_bin(az);
+
+                u64 ki = KEY_INF, kj = KEY_INF;
+                // seeds from the previous pass: the two points it chose are real target points => valid bounds
+                if (pki != KEY_INF) {
+                    const int s = key_ring(pki), n = key_idx(pki);
+                    const float4 c = __ldg(ptsS + __ldg(rsS + s) + n);
+                    const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
+                    if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
+                }
+                if (pkj != KEY_INF) {
+                    const int s = key_ring(pkj), n = key_idx(pkj);
+                    const float4 c = __ldg(ptsS + __ldg(rsS + s) + n);
+                    const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
+                    if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
+                }
+                // Phase 1 (probe), only while two rings do not yet hold a candidate: rings in order of increasing elevation
+                // gap (levels of doubling tolerance, read from the ring masks), only the query's own azimuth bin of each.
+                if (kj == KEY_INF) {
+                    const float gam_thr = make_window(thr_f, az, D, rho).gam;   // elevation tolerance of the threshold itself
+                    Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq;
+                    u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
+                    for (float lev = 0.0065f; kj == KEY_INF; lev *= 2.0f) {
+                        ws.gam = fminf(lev, gam_thr);
 #pragma unroll
-                    for (int word = 0; word < 4; word++) {
-                        if (word >= W) break;
-                        u64 m = ring_mask(mloS, mhiS, W, word, ws, el) & ~V[word];
-                        V[word] |= m;
-                        while (m && kj == KEY_INF) {
-                            const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1;
-                            merge_key(scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, ws, mx, my, mz, thr_excl, st_seed), ki, kj);
+                        for (int word = 0; word < 4; word++) {
+                            if (word >= W) break;
+                            u64 m = ring_mask(mloS, mhiS, W, word, ws, el) & ~V[word];
+                            V[word] |= m;
+                            while (m && kj == KEY_INF) {
+                                const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1;
+                                merge_key(scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, ws, mx, my, mz, thr_excl, st_seed), ki, kj);
+                            }
                         }
+                        if (!(lev < gam_thr)) break;
                     }
-                    if (!(lev < gam_thr)) break;
                 }
-            }
-            // Phase 2 (exhaustive): every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is
-            // visited exactly once, again nearest elevation first; the bound, the azimuth window and the elevation tolerance
-            // shrink whenever the runner-up improves.
-            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
-#ifdef VELO_ICP_DEBUG
-            const float dbg_si = (ki == KEY_INF) ? -1.f : sqrtf(key_d2(ki)), dbg_sj = (kj == KEY_INF) ? -1.f : sqrtf(key_d2(kj));
-#endif
-            Window w = make_window(bound, az, D, rho);
-            {
-                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                for (float lev = 0.0065f;; lev *= 2.0f) {
-                    const float gcur = fminf(lev, w.gam);
-                    Window wl = w; wl.gam = gcur;
+                // Phase 2 (exhaustive): every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is
+                // visited exactly once, nearest elevation first; the bound, the azimuth window and the elevation tolerance
+                // shrink whenever the runner-up improves.
+                float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+                Window w = make_window(bound, az, D, rho);
+                {
+                    u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
+                    for (float lev = 0.0065f;; lev *= 2.0f) {
+                        const float gcur = fminf(lev, w.gam);
+                        Window wl = w; wl.gam = gcur;
 #pragma unroll
-                    for (int word = 0; word < 4; word++) {
-                        if (word >= W) break;
-                        u64 m = ring_mask(mloS, mhiS, W, word, wl, el) & ~V[word];
-                        V[word] |= m;
-                        while (m) {
-                            const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
-                            // a ring that already holds the best candidate only needs points that beat its own candidate
-                            const bool own = (ki != KEY_INF) && (s == key_ring(ki));
-                            const float bnd_s = own ? key_d2(ki) : bound;
-                            Window wr;
-                            if (!ring_test(sbS + s * VELO_SECTORS, w, az, el, rho, bnd_s, wr)) continue;
-                            const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, wr, mx, my, mz, thr_excl, st_exh);
-                            st_rings++;
-                            if (k == KEY_INF) continue;
-                            const u64 oj = kj;
-                            merge_key(k, ki, kj);
-                            if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+                        for (int word = 0; word < 4; word++) {
+                            if (word >= W) break;
+                            u64 m = ring_mask(mloS, mhiS, W, word, wl, el) & ~V[word];
+                            V[word] |= m;
+                            while (m) {
+                                const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
+                                // a ring that already holds the best candidate only needs points that beat its own candidate
+                                const bool own = (ki != KEY_INF) && (s == key_ring(ki));
+                                const float bnd_s = own ? key_d2(ki) : bound;
+                                Window wr;
+                                if (!ring_test(sbS + s * VELO_SECTORS, w, az, el, rho, bnd_s, wr)) continue;
+                                const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, wr, mx, my, mz, thr_excl, st_exh);
+                                st_rings++;
+                                if (k == KEY_INF) continue;
+                                const u64 oj = kj;
+                                merge_key(k, ki, kj);
+                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+                            }
                         }
+                        if (!(gcur < w.gam)) break;      // all rings within the (possibly reduced) tolerance have been visited
                     }
-                    if (!(gcur < w.gam)) break;      // all rings within the (possibly reduced) tolerance have been visited
                 }
-            }
+                pki = ki; pkj = kj;
 
-            velo_icp_corr rec;
-            rec.src_ring = sm; rec.src_idx = smi; rec.np_s_i = -1; rec.np_i = 0; rec.np_s_j = -1; rec.np_j = 0; rec.np_k = -1; rec.kept = 0;
-            rec.normal[0] = rec.normal[1] = rec.normal[2] = 0.f; rec.v0[0] = rec.v0[1] = rec.v0[2] = 0.f; rec.residual = 0.0;
-            if (ki != KEY_INF) { rec.np_s_i = key_ring(ki); rec.np_i = key_idx(ki); }
-            if (kj != KEY_INF) { rec.np_s_j = key_ring(kj); rec.np_j = key_idx(kj); }
-            if (ki != KEY_INF && kj != KEY_INF) {                        // velo.h:849-851
-                const int si = rec.np_s_i, ni = rec.np_i, sj = rec.np_s_j, nj = rec.np_j;
-                const int ri0 = __ldg(rsS + si), Ln = __ldg(rsS + si + 1) - ri0;
-                const int k1 = (ni + 1) % Ln, k2 = (ni - 1 + Ln) % Ln;  // velo.h:852-863
-                const float4 a1 = __ldg(ptsS + ri0 + k1), a2 = __ldg(ptsS + ri0 + k2);
-                const float n1 = d2f(a1.x, a1.y, a1.z, mx, my, mz), n2 = d2f(a2.x, a2.y, a2.z, mx, my, mz);
-                const int nk = (n1 < n2) ? k1 : k2;
-                rec.np_k = nk;
-                const float4 v0 = __ldg(ptsS + ri0 + ni), v1 = __ldg(ptsS + __ldg(rsS + sj) + nj), v2 = (n1 < n2) ? a1 : a2;
-                // Eigen::Vector3f (v1-v0).cross(v2-v0), norm(), operator/= (velo.h:868-874)
-                const float ax = __fsub_rn(v1.x, v0.x), ay = __fsub_rn(v1.y, v0.y), az3 = __fsub_rn(v1.z, v0.z);
-                const float bx = __fsub_rn(v2.x, v0.x), by = __fsub_rn(v2.y, v0.y), bz = __fsub_rn(v2.z, v0.z);
-                float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az3, by));
-                float ny = __fsub_rn(__fmul_rn(az3, bx), __fmul_rn(ax, bz));
-                float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
-                const float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(nx, nx), __fadd_rn(__fmul_rn(ny, ny), __fmul_rn(nz, nz))));
-                rec.v0[0] = v0.x; rec.v0[1] = v0.y; rec.v0[2] = v0.z;
-                if (nn < U.norm_thr_f) { rec.kept = 2; }                 // velo.h:873
-                else {
-                    nx = __fdiv_rn(nx, nn); ny = __fdiv_rn(ny, nn); nz = __fdiv_rn(nz, nn);
-                    rec.normal[0] = nx; rec.normal[1] = ny; rec.normal[2] = nz;
-                    // cost3DPD (costfunctions.h:40-53): M = R p; M += t - o; r = M . n
-                    const double dnx = nx, dny = ny, dnz = nz;
-                    const double m0 = y0 + (P.t[0] - (double)v0.x), m1 = y1 + (P.t[1] - (double)v0.y), m2 = y2 + (P.t[2] - (double)v0.z);
-                    res = m0 * dnx + m1 * dny + m2 * dnz;
+                velo_icp_corr rec;
+                rec.src_ring = sm; rec.src_idx = smi; rec.np_s_i = -1; rec.np_i = 0; rec.np_s_j = -1; rec.np_j = 0; rec.np_k = -1; rec.kept = 0;
+                rec.normal[0] = rec.normal[1] = rec.normal[2] = 0.f; rec.v0[0] = rec.v0[1] = rec.v0[2] = 0.f; rec.residual = 0.0;
+                if (ki != KEY_INF) { rec.np_s_i = key_ring(ki); rec.np_i = key_idx(ki); }
+                if (kj != KEY_INF) { rec.np_s_j = key_ring(kj); rec.np_j = key_idx(kj); }
+                if (ki != KEY_INF && kj != KEY_INF) {                        // velo.h:849-851
+                    const int si = rec.np_s_i, ni = rec.np_i, sj = rec.np_s_j, nj = rec.np_j;
+                    const int ri0 = __ldg(rsS + si), Ln = __ldg(rsS + si + 1) - ri0;
+                    const int k1 = (ni + 1 == Ln) ? 0 : ni + 1, k2 = (ni == 0) ? Ln - 1 : ni - 1;   // (np_i +- 1) mod n, velo.h:852-854
+                    const float4 a1 = __ldg(ptsS + ri0 + k1), a2 = __ldg(ptsS + ri0 + k2);
+                    const float n1 = d2f(a1.x, a1.y, a1.z, mx, my, mz), n2 = d2f(a2.x, a2.y, a2.z, mx, my, mz);
+                    const int nk = (n1 < n2) ? k1 : k2;                      // velo.h:859-863
+                    rec.np_k = nk;
+                    const float4 v0 = __ldg(ptsS + ri0 + ni), v1 = __ldg(ptsS + __ldg(rsS + sj) + nj), v2 = (n1 < n2) ? a1 : a2;
+                    // Eigen::Vector3f (v1-v0).cross(v2-v0), norm(), operator/= (velo.h:868-874)
+                    const float ax = __fsub_rn(v1.x, v0.x), ay = __fsub_rn(v1.y, v0.y), az3 = __fsub_rn(v1.z, v0.z);
+                    const float bx = __fsub_rn(v2.x, v0.x), by = __fsub_rn(v2.y, v0.y), bz = __fsub_rn(v2.z, v0.z);
+                    float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az3, by));
+                    float ny = __fsub_rn(__fmul_rn(az3, bx), __fmul_rn(ax, bz));
+                    float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+                    const float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(nx, nx), __fadd_rn(__fmul_rn(ny, ny), __fmul_rn(nz, nz))));
+                    rec.v0[0] = v0.x; rec.v0[1] = v0.y; rec.v0[2] = v0.z;
+                    if (nn < U.norm_thr_f) { rec.kept = 2; }                 // velo.h:873
+                    else {
+                        nx = __fdiv_rn(nx, nn); ny = __fdiv_rn(ny, nn); nz = __fdiv_rn(nz, nn);
+                        rec.normal[0] = nx; rec.normal[1] = ny; rec.normal[2] = nz;
+                        // cost3DPD (costfunctions.h:40-53): M = R p; M += t - o; r = M . n
+                        const double dnx = nx, dny = ny, dnz = nz;
+                        const double m0 = y0 + (P.pose.t[0] - (double)v0.x), m1 = y1 + (P.pose.t[1] - (double)v0.y), m2 = y2 + (P.pose.t[2] - (double)v0.z);
+                        res = m0 * dnx + m1 * dny + m2 * dnz;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const double *d = P.dR + 9 * k;
-                        const double e0 = d[0] * x0 + d[1] * x1 + d[2] * x2, e1 = d[3] * x0 + d[4] * x1 + d[5] * x2, e2 = d[6] * x0 + d[7] * x1 + d[8] * x2;
-                        J[k] = e0 * dnx + e1 * dny + e2 * dnz;
+                        for (int k = 0; k < 3; k++) {
+                            const double *d = P.pose.dR + 9 * k;
+                            const double e0 = d[0] * x0 + d[1] * x1 + d[2] * x2, e1 = d[3] * x0 + d[4] * x1 + d[5] * x2, e2 = d[6] * x0 + d[7] * x1 + d[8] * x2;
+                            J[k] = e0 * dnx + e1 * dny + e2 * dnz;
+                        }
+                        J[3] = dnx; J[4] = dny; J[5] = dnz;
+                        // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
+                        const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
+                        rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
+                        rho0h = 0.5 * U.weight * bb * log(sum);
+                        rec.kept = 1; rec.residual = res;
+                        kept = true;
                     }
-                    J[3] = dnx; J[4] = dny; J[5] = dnz;
-                    // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
-                    const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
-                    rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
-                    rho0h = 0.5 * U.weight * bb * log(sum);
-                    rec.kept = 1; rec.residual = res;
-                    kept = true;
+                }
+                if (corr && ps == NP - 1) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
+#ifdef VELO_ICP_DEBUG   /* tools/icp_debug_hist.py: per-query search statistics instead of the Jacobian */
+                    rec.jacobian[3] = st_seed; rec.jacobian[4] = st_exh; rec.jacobian[5] = st_rings + 1000.0 * st_mask;
+#endif
+                    corr[q] = rec;
                 }
             }
-            if (corr) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
-#ifdef VELO_ICP_DEBUG   /* tools/icp_stats.py --debug: per-query search statistics instead of the translation Jacobian */
-                rec.jacobian[0] = dbg_si; rec.jacobian[1] = dbg_sj; rec.jacobian[2] = (kj == KEY_INF) ? -1.0 : sqrt((double)key_d2(kj));
-                rec.jacobian[3] = st_seed - dbg0; rec.jacobian[4] = st_exh - dbg1; rec.jacobian[5] = (st_rings - dbg2) + 1000.0 * (st_mask - dbg3);
-#endif
-                corr[q] = rec;
+            // ---- normal equations of this pass: rows of the 32 lanes -> the 28+28 sums owned by lanes 0..27
+            double acc = 0.0, raw = 0.0;
+            warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
+            if (lane < 28) { s_acc[wid][ps][lane] += acc; s_acc[wid][ps][28 + lane] += raw; }
+            int c_kept = kept ? 1 : 0;
+            for (int o = 16; o > 0; o >>= 1) {
+                c_kept += __shfl_down_sync(FULL, c_kept, o);
+                st_seed += __shfl_down_sync(FULL, st_seed, o); st_exh += __shfl_down_sync(FULL, st_exh, o);
+                st_rings += __shfl_down_sync(FULL, st_rings, o); st_mask += __shfl_down_sync(FULL, st_mask, o);
+            }
+            if (lane == 0) {
+                atomicAdd(&s_stat[ps][0], (u64)c_kept); atomicAdd(&s_stat[ps][1], (u64)st_seed); atomicAdd(&s_stat[ps][2], (u64)st_exh);
+                atomicAdd(&s_stat[ps][3], (u64)st_rings); atomicAdd(&s_stat[ps][4], (u64)st_mask);
             }
         }
-        kept_local += kept ? 1 : 0;
-        warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
     }
-    // reduce
-    for (int o = 16; o > 0; o >>= 1) kept_local += __shfl_down_sync(FULL, kept_local, o);
-    if (lane == 0 && kept_local) atomicAdd(&s_kept, kept_local);
-    for (int o = 16; o > 0; o >>= 1) {
-        st_seed += __shfl_down_sync(FULL, st_seed, o); st_exh += __shfl_down_sync(FULL, st_exh, o);
-        st_rings += __shfl_down_sync(FULL, st_rings, o); st_mask += __shfl_down_sync(FULL, st_mask, o);
+    __syncthreads();
+    // per-CTA partials, fixed warp order
+    for (int i = tid; i < NP * 56; i += blockDim.x) {
+        const int ps = i / 56, t = i % 56;
+        double s = 0.0;
+        for (int wq = 0; wq < ICP_THREADS / 32; wq++) s += s_acc[wq][ps][t];
+        pbase[ps * 64 + t] = s;
     }
-    if (lane == 0) { atomicAdd(&s_stat[0], (u64)st_seed); atomicAdd(&s_stat[1], (u64)st_exh); atomicAdd(&s_stat[2], (u64)st_rings); atomicAdd(&s_stat[3], (u64)st_mask); }
-    double *pout = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64;
-    block_neq_finish(s_red, acc, raw, pout);
-    if (tid == 0) {
-        pout[56] = (double)s_kept; pout[57] = (double)s_kept; pout[58] = (double)(q1 > q0 ? q1 - q0 : 0);
-        for (int i = 0; i < 4; i++) pout[59 + i] = (double)s_stat[i];
+    if (tid < NP) {
+        double *po = pbase + tid * 64;
+        po[56] = (double)s_stat[tid][0]; po[57] = (double)s_stat[tid][0]; po[58] = (double)(q1 > q0 ? q1 - q0 : 0);
+        po[59] = (double)s_stat[tid][1]; po[60] = (double)s_stat[tid][2]; po[61] = (double)s_stat[tid][3]; po[62] = (double)s_stat[tid][4]; po[63] = 0.0;
     }
 }
 
-// fixed-order sum of the per-CTA partials of one unit: out[u][0..58]
-__global__ void k_neq_reduce(const double *__restrict__ partial, double *__restrict__ out, int ctas) {
-    const int u = blockIdx.x, t = threadIdx.x;
+// fixed-order sum of the per-CTA partials of one (unit, pass): out[unit][pass][0..62]
+__global__ void k_neq_reduce(const double *__restrict__ partial, double *__restrict__ out, int ctas, int out_stride_passes) {
+    const int u = blockIdx.x, ps = blockIdx.y, t = threadIdx.x;
     if (t >= VELO_NEQ_STRIDE) return;
     double s = 0.0;
-    if (t < 63) for (int c = 0; c < ctas; c++) s += partial[((size_t)u * ctas + c) * 64 + t];
-    out[(size_t)u * VELO_NEQ_STRIDE + t] = s;
+    if (t < 63) for (int c = 0; c < ctas; c++) s += partial[(((size_t)u * ctas + c) * VELO_MAX_PASSES + ps) * 64 + t];
+    out[((size_t)u * out_stride_passes + ps) * VELO_NEQ_STRIDE + t] = s;
 }
 
-void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int ctas,
-                double *partial, double *out, velo_icp_corr *corr) {
+void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
+                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr) {
     if (n_units <= 0) return;
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
     k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, corr);
     if (L.post) L.post(L.user, VK_ICP_PASS);
+    dim3 g2(n_units, n_pass);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);
-    k_neq_reduce<<<n_units, 64, 0, L.stream>>>(partial, out, ctas);
+    k_neq_reduce<<<g2, 64, 0, L.stream>>>(partial, out, ctas, out_stride_passes);
     if (L.post) L.post(L.user, VK_NEQ_REDUCE);
 }

@@ -107,6 +107,7 @@ def algorithmic_bytes(abi, prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_
 def run_ours(args, rank, world, local_rank):
     velo = importlib.import_module("vision-enhanced-lidar-odometry_b200")
     api, synth, abi = velo.api, velo.synth, velo.abi
+    shard = importlib.import_module("vision-enhanced-lidar-odometry_b200.shard")
     import numpy as np
     dist = None
     if world > 1:
@@ -115,10 +116,11 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")   # the host gather of per-frame normal equations never touches NCCL
     T = args.frames
     P, Tr, w, h = synth.calib_raw(args.rig)
     cal = api.calib_from_kitti(P, Tr, w, h)
-    prm = api.default_params(max_slots=T + 1, max_points=131072, max_rings=96, max_features=args.features, max_matches=args.features,
+    prm = api.default_params(max_slots=T + 1, max_points=131072, max_rings=64, max_features=args.features, max_matches=args.features,
                              icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
     ctx = api.Context(prm, cal, device=local_rank)
     pool = api.PinnedPool()
@@ -177,10 +179,8 @@ def run_ours(args, rank, world, local_rank):
         ctx.batch_upload(0, batch)
         ctx.batch_run(0, T + 1)
         ctx.batch_download(0, T + 1, icp, vis, hd, nh)
-        if dist is not None:   # host gather of the per-frame normal equations (the only cross-GPU traffic)
-            import torch
-            g = [torch.empty_like(torch.from_numpy(icp)) for _ in range(world)] if rank == 0 else None
-            dist.gather(torch.from_numpy(icp).cuda(), [x.cuda() for x in g] if g else None, dst=0)
+        if dist is not None:   # host gather of the per-frame normal equations (the only cross-GPU traffic; gloo, CPU tensors)
+            gathered = shard.gather_rows(dist, icp[1:], dst=0, group=host_group)
     e2e_ms = ctx.timer_end()
     e2e_wall = (time.perf_counter() - t0) * 1e3
     barrier()
@@ -272,7 +272,7 @@ def run_reference(args, rank, world):
     api, synth = velo.api, velo.synth
     P, Tr, w, h = synth.calib_raw(args.rig)
     cal = api.calib_from_kitti(P, Tr, w, h)
-    prm = api.default_params(max_slots=2, max_points=131072, max_rings=96, max_features=args.features, max_matches=args.features,
+    prm = api.default_params(max_slots=2, max_points=131072, max_rings=64, max_features=args.features, max_matches=args.features,
                              icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
     cores = os.cpu_count() or 1
     times = []

@@ -50,7 +50,8 @@ def build_gpu(force=False, verbose=False):
         if os.path.isfile(GPU_LIB):
             return GPU_LIB  # prebuilt library shipped with the snapshot
         raise RuntimeError("nvcc not found and libvelo_gpu.so is not built")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    extra = os.environ.get("VELO_NVCC_EXTRA", "").split()      # tuning experiments only (tools/)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + gpu_sources() + ["-o", GPU_LIB]
     subprocess.run(cmd, check=True)
     return GPU_LIB

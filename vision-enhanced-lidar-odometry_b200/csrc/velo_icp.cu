@@ -12,7 +12,12 @@
 // only inside the azimuth window asin(b/|q_xy|), b = current bound on sqrt(d2_j).
 #include "velo_common.cuh"
 
+#ifndef ICP_THREADS
 #define ICP_THREADS 128
+#endif
+#ifndef ICP_MIN_BLOCKS
+#define ICP_MIN_BLOCKS 6
+#endif
 #define KEY_INF 0xFFFFFFFFFFFFFFFFull
 
 __device__ __forceinline__ u64 make_key(float d2, int ring, int idx) {
@@ -133,7 +138,7 @@ __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 
 // grid = (ctas per unit, n_units).  A unit is one frame pair with up to VELO_MAX_PASSES supplied poses (the ICP passes of
 // frameToFrame, velo.h:616,800).  One thread = one query point at a time, looping over the passes: the correspondence of
 // pass p (two real target points) seeds pass p+1 with an immediately tight bound, so only the first pass needs the probe.
-__global__ void __launch_bounds__(ICP_THREADS, 6) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
+__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
                                                           double *__restrict__ partial, velo_icp_corr *__restrict__ corr) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
@@ -195,34 +200,35 @@ __global__ void __launch_bounds__(ICP_THREADS, 6) k_icp_pass(DevBuffers B, DevCa
             bool kept = false;
             double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
             int st_seed = 0, st_exh = 0, st_rings = 0, st_mask = 0;
+            // (all 32 lanes run the pass; lanes without a query are born finished so that the warp votes below stay uniform)
+            // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
+            double y0, y1, y2;
+            if (!P.pose.small_angle) {
+                const double c0 = __dsub_rn(__dmul_rn(P.pose.u[1], x2), __dmul_rn(P.pose.u[2], x1));
+                const double c1 = __dsub_rn(__dmul_rn(P.pose.u[2], x0), __dmul_rn(P.pose.u[0], x2));
+                const double c2 = __dsub_rn(__dmul_rn(P.pose.u[0], x1), __dmul_rn(P.pose.u[1], x0));
+                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.pose.u[0], x0), __dmul_rn(P.pose.u[1], x1)), __dmul_rn(P.pose.u[2], x2));
+                const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.pose.c));
+                y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.pose.c), __dmul_rn(c0, P.pose.s)), __dmul_rn(P.pose.u[0], tmp));
+                y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.pose.c), __dmul_rn(c1, P.pose.s)), __dmul_rn(P.pose.u[1], tmp));
+                y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.pose.c), __dmul_rn(c2, P.pose.s)), __dmul_rn(P.pose.u[2], tmp));
+            } else {
+                y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.pose.w[1], x2), __dmul_rn(P.pose.w[2], x1)));
+                y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.pose.w[2], x0), __dmul_rn(P.pose.w[0], x2)));
+                y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.pose.w[0], x1), __dmul_rn(P.pose.w[1], x0)));
+            }
+            const float mx = __double2float_rn(__dadd_rn(y0, P.pose.t[0]));
+            const float my = __double2float_rn(__dadd_rn(y1, P.pose.t[1]));
+            const float mz = __double2float_rn(__dadd_rn(y2, P.pose.t[2]));
+
+            // ---- pruning geometry of the query in the index frame of the target scan
+            float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
+            const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float az = atan2f(vy, vx), el = atan2f(vz, D);
+            const int bq = az_bin(az);
+
+            u64 ki = KEY_INF, kj = KEY_INF;
             if (active) {
-                // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
-                double y0, y1, y2;
-                if (!P.pose.small_angle) {
-                    const double c0 = __dsub_rn(__dmul_rn(P.pose.u[1], x2), __dmul_rn(P.pose.u[2], x1));
-                    const double c1 = __dsub_rn(__dmul_rn(P.pose.u[2], x0), __dmul_rn(P.pose.u[0], x2));
-                    const double c2 = __dsub_rn(__dmul_rn(P.pose.u[0], x1), __dmul_rn(P.pose.u[1], x0));
-                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.pose.u[0], x0), __dmul_rn(P.pose.u[1], x1)), __dmul_rn(P.pose.u[2], x2));
-                    const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.pose.c));
-                    y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.pose.c), __dmul_rn(c0, P.pose.s)), __dmul_rn(P.pose.u[0], tmp));
-                    y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.pose.c), __dmul_rn(c1, P.pose.s)), __dmul_rn(P.pose.u[1], tmp));
-                    y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.pose.c), __dmul_rn(c2, P.pose.s)), __dmul_rn(P.pose.u[2], tmp));
-                } else {
-                    y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.pose.w[1], x2), __dmul_rn(P.pose.w[2], x1)));
-                    y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.pose.w[2], x0), __dmul_rn(P.pose.w[0], x2)));
-                    y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.pose.w[0], x1), __dmul_rn(P.pose.w[1], x0)));
-                }
-                const float mx = __double2float_rn(__dadd_rn(y0, P.pose.t[0]));
-                const float my = __double2float_rn(__dadd_rn(y1, P.pose.t[1]));
-                const float mz = __double2float_rn(__dadd_rn(y2, P.pose.t[2]));
-
-                // ---- pruning geometry of the query in the index frame of the target scan
-                float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
-                const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
-                const float az = atan2f(vy, vx), el = atan2f(vz, D);
-                const int bq = az_bin(az);
-
-                u64 ki = KEY_INF, kj = KEY_INF;
                 // seeds from the previous pass: the two points it chose are real target points => valid bounds
                 if (pki != KEY_INF) {
                     const int s = key_ring(pki), n = key_idx(pki);
@@ -257,39 +263,59 @@ __global__ void __launch_bounds__(ICP_THREADS, 6) k_icp_pass(DevBuffers B, DevCa
                         if (!(lev < gam_thr)) break;
                     }
                 }
-                // Phase 2 (exhaustive): every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is
-                // visited exactly once, nearest elevation first; the bound, the azimuth window and the elevation tolerance
-                // shrink whenever the runner-up improves.
-                float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
-                Window w = make_window(bound, az, D, rho);
-                {
-                    u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                    for (float lev = 0.0065f;; lev *= 2.0f) {
-                        const float gcur = fminf(lev, w.gam);
-                        Window wl = w; wl.gam = gcur;
-#pragma unroll
-                        for (int word = 0; word < 4; word++) {
-                            if (word >= W) break;
-                            u64 m = ring_mask(mloS, mhiS, W, word, wl, el) & ~V[word];
-                            V[word] |= m;
-                            while (m) {
-                                const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
-                                // a ring that already holds the best candidate only needs points that beat its own candidate
-                                const bool own = (ki != KEY_INF) && (s == key_ring(ki));
-                                const float bnd_s = own ? key_d2(ki) : bound;
-                                Window wr;
-                                if (!ring_test(sbS + s * VELO_SECTORS, w, az, el, rho, bnd_s, wr)) continue;
-                                const u64 k = scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, wr, mx, my, mz, thr_excl, st_exh);
-                                st_rings++;
-                                if (k == KEY_INF) continue;
-                                const u64 oj = kj;
-                                merge_key(k, ki, kj);
-                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+            }
+            // Phase 2 (exhaustive): every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is visited
+            // exactly once, nearest elevation first (levels of doubling tolerance; a single level when the bound is already
+            // tight); the bound, the azimuth window and the elevation tolerance shrink whenever the runner-up improves.
+            // Written as a warp-synchronous "advance / scan" loop: lanes first advance (cheap ring tests) until each holds a
+            // candidate range, then all of them scan together, so the distance loop runs converged.
+            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+            Window w = make_window(bound, az, D, rho);
+            {
+                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
+                u64 m = 0ull;
+                int word = 0, p0 = 0, e0 = 0, p1 = 0, e1 = 0, s_cur = 0;
+                float lev = 0.f, gcur = 0.f;
+                bool started = false, have = false, fin = !active;
+                for (;;) {
+                    while (!have && !fin) {
+                        if (m == 0ull) {                                   // next (level, word)
+                            if (started && word + 1 < W) word++;
+                            else {
+                                if (started && !(gcur < w.gam)) { fin = true; break; }   // every ring within the tolerance was visited
+                                lev = started ? lev * 2.0f : (w.gam <= 0.03f ? 8.0f : 0.0065f);
+                                started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
+                            Window wl = w; wl.gam = gcur;
+                            m = ring_mask(mloS, mhiS, W, word, wl, el) & ~V[word];
+                            V[word] |= m;
+                            continue;
                         }
-                        if (!(gcur < w.gam)) break;      // all rings within the (possibly reduced) tolerance have been visited
+                        const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
+                        // a ring that already holds the best candidate only needs points that beat its own candidate
+                        const bool own = (ki != KEY_INF) && (s == key_ring(ki));
+                        Window wr;
+                        if (!ring_test(sbS + s * VELO_SECTORS, w, az, el, rho, own ? key_d2(ki) : bound, wr)) continue;
+                        const int *cs = csS + s * (VELO_AZ_BINS + 1);
+                        if (!wr.wrapped) { p0 = __ldg(cs + wr.b0); e0 = __ldg(cs + wr.b1 + 1); p1 = 0; e1 = 0; }
+                        else { p0 = __ldg(cs + wr.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + wr.b1 + 1); }
+                        s_cur = s; have = true;
+                    }
+                    if (!__any_sync(FULL, have)) break;
+                    if (have) {
+                        float bd = thr_excl; int bi = -1;
+                        scan_range(sorted, p0, e0, mx, my, mz, bd, bi, st_exh);
+                        if (p1 < e1) scan_range(sorted, p1, e1, mx, my, mz, bd, bi, st_exh);
+                        st_rings++; have = false;
+                        if (bi >= 0) {
+                            const u64 oj = kj;
+                            merge_key(make_key(bd, s_cur, bi), ki, kj);
+                            if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+                        }
                     }
                 }
+            }
+            if (active) {
                 pki = ki; pkj = kj;
 
                 velo_icp_corr rec;

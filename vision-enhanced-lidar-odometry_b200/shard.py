@@ -18,19 +18,19 @@ def halo_range(total_frames, world, rank):
     return start - 1, count + 1
 
 
-def gather_rows(dist, local, dst=0):
+def gather_rows(dist, local, dst=0, group=None):
     """Gather [count_r, ...] arrays of every rank to `dst` (torch.distributed, any backend) and concatenate in
     rank order.  Returns the concatenation on dst, None elsewhere."""
     import torch
     t = torch.from_numpy(np.ascontiguousarray(local))
     world, rank = dist.get_world_size(), dist.get_rank()
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64))
+    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64), group=group)
     mx = int(max(int(c.item()) for c in counts))
     pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype)
     pad[: t.shape[0]] = t
     out = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, out, dst=dst)
+    dist.gather(pad, out, dst=dst, group=group)
     if rank != dst:
         return None
     return np.concatenate([o[: int(c.item())].numpy() for o, c in zip(out, counts)], axis=0)

@@ -237,7 +237,7 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &B.matches, S * C * MM * 2)); CKC(dalloc(ctx, &B.n_matches, S * C));
     // units / normal equations
     ctx->icp_partial_ctas = 296;
-    if (prm->max_icp_passes > VELO_MAX_PASSES) { velo_gpu_destroy(ctx); return fail(nullptr, VELO_ERR_INVALID_ARG, "max_icp_passes exceeds VELO_MAX_PASSES (8)"); }
+    if (prm->max_icp_passes > VELO_MAX_PASSES) { velo_gpu_destroy(ctx); return fail(nullptr, VELO_ERR_INVALID_ARG, "max_icp_passes exceeds VELO_MAX_PASSES (6)"); }
     const size_t n_icp_units = S, n_vis_units = S * (size_t)(prm->f2f_iterations > 0 ? prm->f2f_iterations : 1);
     CKC(cudaMallocHost((void **)&ctx->h_icp_units, n_icp_units * sizeof(IcpUnit)));
     CKC(cudaMallocHost((void **)&ctx->h_vis_units, n_vis_units * sizeof(VisUnit)));

@@ -25,9 +25,9 @@
 #define VELO_SECTORS 64
 #define VELO_BINS_PER_SECTOR (VELO_AZ_BINS / VELO_SECTORS)
 #define VELO_MAX_RINGS_HARD 256
-#define VELO_EL_BUCKETS 128         /* elevation buckets of the ring-mask tables */
-#define VELO_EL_MIN (-0.62f)        /* rad; elevations outside [EL_MIN, EL_MAX] clamp to the edge buckets (still conservative) */
-#define VELO_EL_MAX (0.34f)
+#define VELO_EL_BUCKETS 256         /* elevation buckets of the ring-mask tables */
+#define VELO_EL_MIN (-0.47f)        /* rad; elevations outside [EL_MIN, EL_MAX] clamp to the edge buckets (still conservative) */
+#define VELO_EL_MAX (0.10f)
 #define VELO_IDX_BITS 20            /* index-in-ring bits of the neighbour key */
 #define VELO_RING_BITS 12
 
@@ -66,7 +66,7 @@ struct PosePack {
     int pad;
 };
 
-#define VELO_MAX_PASSES 8        /* ICP passes per frame pair in one launch (f2f_iterations * icp_iterations = 6) */
+#define VELO_MAX_PASSES 6        /* ICP passes per frame pair in one launch (f2f_iterations * icp_iterations = 6) */
 
 struct IcpPass {
     PosePack pose;

@@ -13,10 +13,10 @@
 #include "velo_common.cuh"
 
 #ifndef ICP_THREADS
-#define ICP_THREADS 128
+#define ICP_THREADS 256
 #endif
 #ifndef ICP_MIN_BLOCKS
-#define ICP_MIN_BLOCKS 6
+#define ICP_MIN_BLOCKS 3
 #endif
 #define KEY_INF 0xFFFFFFFFFFFFFFFFull
 

@@ -79,8 +79,8 @@ __device__ __forceinline__ void warp_accum(double *s_rows, const double J[6], do
         for (unsigned m = mask; m; m &= m - 1) {
             const double *rq = s_rows + (__ffs(m) - 1) * NEQ_ROW;
             const double p = rq[a] * rq[b];
-            if (lane == 27) { raw += 0.5 * p; acc += rq[8]; }
-            else { raw += p; acc += rq[7] * p; }
+            if (lane == 27) { raw = fma(0.5, p, raw); acc += rq[8]; }     // explicit fma: the sums are not parity-critical (1e-4)
+            else { raw += p; acc = fma(rq[7], p, acc); }
         }
     }
 }

@@ -89,10 +89,10 @@ __device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, cons
 // Per-ring pruning from the sector boxes {elev lo, elev hi, range min, range max} of the ring inside the window's sectors.
 // With rq, rp the ranges from the index origin and `angle` the angle between the two directions,
 //     d2(q,p) = (rq - rp)^2 + 4 rq rp sin^2(angle/2),     sin^2(angle/2) = sin^2(de/2) + cos(eq) cos(ep) sin^2(daz/2)   (haversine)
-// so (a) d2 >= dr^2 + 4 rq rlo sin^2(gap/2) =: lb2 (ring skipped when lb2 > bound) and (b) a point within the bound has
-//     sin^2(daz/2) <= (bound - dr^2) / (4 rq rlo cos(eq) cos(ep))   -> a narrower azimuth window for this ring.
-// Every quantity is deflated/inflated so that float error in this pruning math can only keep extra candidates.
-__device__ __forceinline__ bool ring_test(const float4 *__restrict__ sb4, const Window &w, float az, float el, float rho, float bnd, Window &wr) {
+// so d2 >= dr^2 + 4 rq rlo sin^2(gap/2) =: lb2 and the ring is skipped when lb2 > bound.  (A per-ring narrowing of the
+// azimuth window from the same inequality was measured to cost more instructions than the candidates it saves: distance
+// evaluations are cheap here, control flow is not.)  Every quantity is deflated/inflated so that float error in this pruning math can only keep extra candidates.
+__device__ __forceinline__ bool ring_test(const float4 *__restrict__ sb4, const Window &w, float el, float rho, float bnd) {
     float elo = CUDART_INF_F, ehi = -CUDART_INF_F, rlo = CUDART_INF_F, rhi = -CUDART_INF_F;
     int sa = w.b0 / VELO_BINS_PER_SECTOR, sb = w.b1 / VELO_BINS_PER_SECTOR;
     if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
@@ -108,19 +108,7 @@ __device__ __forceinline__ bool ring_test(const float4 *__restrict__ sb4, const 
     const float sh = h * (1.0f - h * h * (1.0f / 6.0f));           // <= sin(h) for 0 <= h <= 1
     const float rr = 4.0f * rho * fmaxf(rlo, 0.0f) * (1.0f - 1e-5f);
     const float dr2 = dr * dr * (1.0f - 1e-5f);
-    if ((dr2 + rr * sh * sh) * (1.0f - 1e-4f) > bnd) return false;
-    wr = w;
-    const float em = fmaxf(fabsf(elo), fabsf(ehi));
-    const float cc = (1.0f - 0.5f * el * el) * (1.0f - 0.5f * em * em) * (1.0f - 1e-5f);   // <= cos(eq) cos(ep)
-    if (cc > 0.1f && rr > 1e-3f) {
-        const float rem = bnd * (1.0f + 2e-5f) + 1e-7f - dr2;
-        const float s2 = fmaxf(rem, 0.0f) / (rr * cc);
-        if (s2 < 0.8f) {
-            const float half = 2.0f * asin_ub(sqrtf(s2) * (1.0f + 1e-5f)) + 2e-5f;
-            if (half < w.half) set_bins(wr, az, half);
-        }
-    }
-    return true;
+    return !((dr2 + rr * sh * sh) * (1.0f - 1e-4f) > bnd);
 }
 // candidate rings (64-ring word `word`) whose elevation interval in a sector of the window can come within w.gam of el
 __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 *__restrict__ mhi, int W, int word, const Window &w, float el) {
@@ -244,7 +232,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 }
                 // Phase 1 (probe), only while two rings do not yet hold a candidate: rings in order of increasing elevation
                 // gap (levels of doubling tolerance, read from the ring masks), only the query's own azimuth bin of each.
+#ifdef EXP_NO_PROBE
+                if (false) {
+#else
                 if (kj == KEY_INF) {
+#endif
                     const float gam_thr = make_window(thr_f, az, D, rho).gam;   // elevation tolerance of the threshold itself
                     Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq;
                     u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
@@ -276,7 +268,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 u64 m = 0ull;
                 int word = 0, p0 = 0, e0 = 0, p1 = 0, e1 = 0, s_cur = 0;
                 float lev = 0.f, gcur = 0.f;
+#ifdef EXP_NO_PHASE2
+                bool started = false, have = false, fin = true;
+#else
                 bool started = false, have = false, fin = !active;
+#endif
                 for (;;) {
                     while (!have && !fin) {
                         if (m == 0ull) {                                   // next (level, word)
@@ -294,11 +290,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
                         // a ring that already holds the best candidate only needs points that beat its own candidate
                         const bool own = (ki != KEY_INF) && (s == key_ring(ki));
-                        Window wr;
-                        if (!ring_test(sbS + s * VELO_SECTORS, w, az, el, rho, own ? key_d2(ki) : bound, wr)) continue;
+                        if (!ring_test(sbS + s * VELO_SECTORS, w, el, rho, own ? key_d2(ki) : bound)) continue;
                         const int *cs = csS + s * (VELO_AZ_BINS + 1);
-                        if (!wr.wrapped) { p0 = __ldg(cs + wr.b0); e0 = __ldg(cs + wr.b1 + 1); p1 = 0; e1 = 0; }
-                        else { p0 = __ldg(cs + wr.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + wr.b1 + 1); }
+                        if (!w.wrapped) { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + w.b1 + 1); p1 = 0; e1 = 0; }
+                        else { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + w.b1 + 1); }
                         s_cur = s; have = true;
                     }
                     if (!__any_sync(FULL, have)) break;
@@ -323,7 +318,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 rec.normal[0] = rec.normal[1] = rec.normal[2] = 0.f; rec.v0[0] = rec.v0[1] = rec.v0[2] = 0.f; rec.residual = 0.0;
                 if (ki != KEY_INF) { rec.np_s_i = key_ring(ki); rec.np_i = key_idx(ki); }
                 if (kj != KEY_INF) { rec.np_s_j = key_ring(kj); rec.np_j = key_idx(kj); }
+#ifdef EXP_NO_EPILOGUE
+                if (false) {
+#else
                 if (ki != KEY_INF && kj != KEY_INF) {                        // velo.h:849-851
+#endif
                     const int si = rec.np_s_i, ni = rec.np_i, sj = rec.np_s_j, nj = rec.np_j;
                     const int ri0 = __ldg(rsS + si), Ln = __ldg(rsS + si + 1) - ri0;
                     const int k1 = (ni + 1 == Ln) ? 0 : ni + 1, k2 = (ni == 0) ? Ln - 1 : ni - 1;   // (np_i +- 1) mod n, velo.h:852-854
@@ -374,7 +373,9 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             }
             // ---- normal equations of this pass: rows of the 32 lanes -> the 28+28 sums owned by lanes 0..27
             double acc = 0.0, raw = 0.0;
+#ifndef EXP_NO_ACCUM
             warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
+#endif
             if (lane < 28) { s_acc[wid][ps][lane] += acc; s_acc[wid][ps][28 + lane] += raw; }
             int c_kept = kept ? 1 : 0;
             for (int o = 16; o > 0; o >>= 1) {

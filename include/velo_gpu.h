@@ -212,6 +212,11 @@ int  velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int
  * has_depth [count][sets][cams][max_features], n_hits [count][sets][cams]; any pointer may be NULL. Synchronises. */
 int  velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *icp_neq, double *vis_neq,
                              int *has_depth, int *n_hits);
+/* the whole front end for a batch in one call: upload (pinned host buffers) -> all stages -> download, with the upload of
+ * chunk c+1 (chunk = frames per chunk, 0 = count/8) overlapping the kernels of chunk c on a second stream.  Slot slot0 is
+ * the halo scan when slot0 == 0 (no frame pair for it).  Synchronises. */
+int  velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
+                             double *icp_neq, double *vis_neq, int *has_depth, int *n_hits);
 /* number of kernel launches issued by this context since creation */
 int  velo_gpu_launch_count(velo_gpu_ctx *ctx, int64_t *launches);
 /* per-slot counts needed to state algorithmic bytes: n_points[count], n_rings[count],

@@ -304,6 +304,11 @@ def test_batched_path_equals_single_frame_path_and_oracle(velo, oracle, calib):
                     assert nh[t, s, cam] == (ohd >= 0).sum()
         npnt, nr, ptot, st = c.batch_counts(0, 3)
         assert np.array_equal(npnt, b.n_points) and np.all(nr == 64) and np.all(st == 0) and np.all(ptot > 10000)
+        # the one-call pipelined path (chunked upload overlapping compute) gives byte-identical results
+        for chunk in (1, 2, 0):
+            icp2 = np.zeros_like(icp); vis2 = np.zeros_like(vis); hd2 = np.zeros_like(hd); nh2 = np.zeros_like(nh)
+            c.batch_frontend(0, b, chunk, icp2, vis2, hd2, nh2)
+            assert icp2.tobytes() == icp.tobytes() and vis2.tobytes() == vis.tobytes() and hd2.tobytes() == hd.tobytes() and nh2.tobytes() == nh.tobytes()
     finally:
         c.close()
 

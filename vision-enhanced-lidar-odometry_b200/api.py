@@ -57,6 +57,7 @@ def lib():
     L.velo_gpu_batch_upload.argtypes = [_P, C.c_int, C.c_int, _P]
     L.velo_gpu_batch_run.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
     L.velo_gpu_batch_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
+    L.velo_gpu_batch_frontend.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]
     L.velo_gpu_batch_counts.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
     L.velo_gpu_launch_count.argtypes = [_P, C.POINTER(C.c_int64)]
     if L.velo_gpu_abi_version() != abi.ABI_VERSION:
@@ -265,6 +266,11 @@ class Context:
 
     def batch_download(self, slot0, count, icp_neq=None, vis_neq=None, has_depth=None, n_hits=None):
         self._ck(self.L.velo_gpu_batch_download(self.h, slot0, count, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
+
+    def batch_frontend(self, slot0, batch, chunk=0, icp_neq=None, vis_neq=None, has_depth=None, n_hits=None):
+        bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
+                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis)
+        self._ck(self.L.velo_gpu_batch_frontend(self.h, slot0, batch.count, C.addressof(bi), chunk, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
 
     def batch_counts(self, slot0, count):
         npnt = np.zeros(count, np.int32); nr = np.zeros(count, np.int32)

@@ -15,7 +15,8 @@ struct ProfRec { int k; cudaEvent_t a, b; };
 
 struct velo_gpu_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
     velo_gpu_params prm;
     velo_gpu_calib cal;
     DevCalib dcal;
@@ -276,6 +277,8 @@ extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VELO_OK;
@@ -596,29 +599,40 @@ static int check_range(velo_gpu_ctx *ctx, int slot0, int count) {
     return VELO_OK;
 }
 
-extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in) {
-    if (!ctx || !in) return VELO_ERR_INVALID_ARG;
-    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
+// copy the inputs of batch entries [i0, i0+count) (slots slot0+i0 ...) to the device on `st`
+static int upload_range(velo_gpu_ctx *ctx, int slot0_all, int i0, int count, const velo_batch_inputs *src, cudaStream_t st) {
+    const int slot0 = slot0_all + i0;
+    velo_batch_inputs inl = *src, *in = &inl;
+    {
+        const size_t C_ = ctx->B.C, F_ = ctx->B.F, MM_ = ctx->B.MM, per_ = VELO_NUM_KP_SETS * C_;
+        if (inl.scans) inl.scans += (size_t)i0 * ctx->prm.max_points * 4;
+        if (inl.n_points) inl.n_points += i0;
+        if (inl.kp) inl.kp += (size_t)i0 * per_ * F_ * 2;
+        if (inl.n_kp) inl.n_kp += (size_t)i0 * per_;
+        if (inl.matches) inl.matches += (size_t)i0 * C_ * MM_ * 2;
+        if (inl.n_matches) inl.n_matches += (size_t)i0 * C_;
+        if (inl.icp_poses) inl.icp_poses += (size_t)i0 * inl.n_passes * 6;
+        if (inl.vis_poses) inl.vis_poses += (size_t)i0 * inl.n_vis_iters * 6;
+    }
     const DevBuffers &B = ctx->B;
     const size_t C = B.C, F = B.F, MM = B.MM;
     if (in->scans && in->n_points) {
         for (int i = 0; i < count; i++) if (in->n_points[i] < 0 || in->n_points[i] > ctx->prm.max_points) return fail(ctx, VELO_ERR_CAPACITY, "scan has more points than max_points");
         CK(cudaMemcpy2DAsync(B.raw + (size_t)slot0 * B.N, (size_t)B.N * sizeof(float4), in->scans, (size_t)ctx->prm.max_points * sizeof(float4),
-                             (size_t)ctx->prm.max_points * sizeof(float4), count, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(B.n_points + slot0, in->n_points, count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                             (size_t)ctx->prm.max_points * sizeof(float4), count, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B.n_points + slot0, in->n_points, count * sizeof(int), cudaMemcpyHostToDevice, st));
         for (int i = 0; i < count; i++) ctx->h_npoints[slot0 + i] = in->n_points[i];
     }
     if (in->kp && in->n_kp) {
         const size_t per = VELO_NUM_KP_SETS * C;
         for (size_t i = 0; i < count * per; i++) if (in->n_kp[i] < 0 || in->n_kp[i] > (int)F) return fail(ctx, VELO_ERR_CAPACITY, "more keypoints than max_features");
-        CK(cudaMemcpyAsync(B.kp + (size_t)slot0 * per * F, in->kp, count * per * F * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(B.n_kp + (size_t)slot0 * per, in->n_kp, count * per * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.kp + (size_t)slot0 * per * F, in->kp, count * per * F * sizeof(float2), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B.n_kp + (size_t)slot0 * per, in->n_kp, count * per * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     if (in->matches && in->n_matches) {
         for (size_t i = 0; i < count * C; i++) if (in->n_matches[i] < 0 || in->n_matches[i] > (int)MM) return fail(ctx, VELO_ERR_CAPACITY, "more matches than max_matches");
-        CK(cudaMemcpyAsync(B.matches + (size_t)slot0 * C * MM * 2, in->matches, count * C * MM * 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(B.n_matches + (size_t)slot0 * C, in->n_matches, count * C * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.matches + (size_t)slot0 * C * MM * 2, in->matches, count * C * MM * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B.n_matches + (size_t)slot0 * C, in->n_matches, count * C * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     if (in->icp_poses && in->pass_iter) {
         if (in->n_passes < 1 || in->n_passes > B.P) return fail(ctx, VELO_ERR_CAPACITY, "n_passes exceeds max_icp_passes");
@@ -630,7 +644,7 @@ extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, co
             init_icp_unit(ctx, u, slot == 0 ? -1 : slot, slot - 1, ctx->prm.icp_skip);
             for (int p = 0; p < in->n_passes; p++) add_icp_pass(ctx, u, in->icp_poses + 6 * ((size_t)i * in->n_passes + p), in->pass_iter[p]);
         }
-        CK(cudaMemcpyAsync(ctx->d_icp_units + slot0, ctx->h_icp_units + slot0, (size_t)count * sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_icp_units + slot0, ctx->h_icp_units + slot0, (size_t)count * sizeof(IcpUnit), cudaMemcpyHostToDevice, st));
     }
     if (in->vis_poses) {
         const int V = ctx->prm.f2f_iterations;
@@ -644,9 +658,16 @@ extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, co
             u->slot1 = slot; u->set1 = 1; u->slot2 = slot - 1; u->set2 = 0; u->iter = it + 1;
             memcpy(u->pose, in->vis_poses + 6 * ((size_t)i * in->n_vis_iters + it), 6 * sizeof(double));
         }
-        CK(cudaMemcpyAsync(ctx->d_vis_units + (size_t)slot0 * V, ctx->h_vis_units + (size_t)slot0 * V, (size_t)count * V * sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_vis_units + (size_t)slot0 * V, ctx->h_vis_units + (size_t)slot0 * V, (size_t)count * V * sizeof(VisUnit), cudaMemcpyHostToDevice, st));
     }
     return VELO_OK;
+}
+
+extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in) {
+    if (!ctx || !in) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return upload_range(ctx, slot0, 0, count, in, ctx->stream);
 }
 
 extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int first_has_prev) {
@@ -694,6 +715,34 @@ extern "C" int velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, 
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     return VELO_OK;
+}
+
+// upload -> run -> download of a whole batch with the uploads of chunk c+1 overlapping the kernels of chunk c
+extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
+                                       double *icp_neq, double *vis_neq, int *has_depth, int *n_hits) {
+    if (!ctx || !in) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (chunk <= 0) chunk = (count + 7) / 8;
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const int nchunks = (count + chunk - 1) / chunk;
+    while ((int)ctx->chunk_ev.size() < nchunks + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    // the copy stream must not overwrite slots that earlier work on the compute stream may still read
+    CK(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * chunk, n = (i0 + chunk <= count) ? chunk : count - i0;
+        int rc = upload_range(ctx, slot0, i0, n, in, ctx->copy_stream);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * chunk, n = (i0 + chunk <= count) ? chunk : count - i0;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        int rc = velo_gpu_batch_run(ctx, slot0 + i0, n, VELO_STAGE_ALL, 1);
+        if (rc) return rc;
+    }
+    return velo_gpu_batch_download(ctx, slot0, count, icp_neq, vis_neq, has_depth, n_hits);
 }
 
 extern "C" int velo_gpu_batch_counts(velo_gpu_ctx *ctx, int slot0, int count, int *n_points, int *n_rings, int *proj_total, int *status) {

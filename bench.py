@@ -98,7 +98,10 @@ def algorithmic_bytes(abi, prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_
     b["assoc_compact"] = F * 4 + F * 4 + hits * 32
     Q = n_fr                                                                                     # icp_skip = 1
     tgt = float(npnt[:-1].sum()); rings_t = float(nr[:-1].sum())
-    b["icp_pass"] = n_passes * (16 * Q / max(prm.icp_skip, 1) + 16 * tgt + rings_t * (4 * (AZ + 1) + 8 * SEC)) + 48 * float(kept) + 512 * n_passes * (len(npnt) - 1)
+    # SURVEY.md §8(d) per-(frame, pass) figure: B_corr = 16Q + 16N + 4 R B + 20Q  (queries, target points, ring x azimuth table, the
+    # 5 int32 correspondence indices).  The fused multi-pass kernel reads the target once per frame PAIR and never writes the
+    # indices, which is why its measured DRAM traffic is far below this number.
+    b["icp_pass"] = n_passes * (36 * Q / max(prm.icp_skip, 1) + 16 * tgt + rings_t * 4 * AZ)
     b["visual_residuals"] = n_vis * (float(nmatch[1:].sum()) * (8 + 2 * 4 + 2 * 16 + 2 * 8)) + 512 * n_vis * (len(npnt) - 1)
     b["neq_reduce"] = 0.0
     return b

@@ -273,13 +273,14 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #else
                 bool started = false, have = false, fin = !active;
 #endif
+                const bool tight = w.gam <= 0.03f;      // seeded / well-probed query: one mask level, window kept for the whole pass
                 for (;;) {
                     while (!have && !fin) {
                         if (m == 0ull) {                                   // next (level, word)
                             if (started && word + 1 < W) word++;
                             else {
                                 if (started && !(gcur < w.gam)) { fin = true; break; }   // every ring within the tolerance was visited
-                                lev = started ? lev * 2.0f : (w.gam <= 0.03f ? 8.0f : 0.0065f);
+                                lev = started ? lev * 2.0f : (tight ? 8.0f : 0.0065f);
                                 started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
                             Window wl = w; wl.gam = gcur;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         if (bi >= 0) {
                             const u64 oj = kj;
                             merge_key(make_key(bd, s_cur, bi), ki, kj);
-                            if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); w = make_window(bound, az, D, rho); }
+                            if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
                         }
                     }
                 }

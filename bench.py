@@ -84,7 +84,7 @@ def algorithmic_bytes(abi, prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_
     """Compulsory traffic per kernel class for one step (DESIGN.md 'Algorithmic bytes'): every input read once,
     every required output written once.  npnt/nr/ptot over the T+1 slots; frame pairs are slots 1..T."""
     C, R = prm.num_cams, 0
-    AZ, SEC = 512, 64
+    AZ, SEC = 1024, 64      # VELO_AZ_BINS, VELO_SECTORS of csrc/velo_dev.cuh
     n_all = float(npnt.sum()); rings_all = float(nr.sum())
     n_fr = float(npnt[1:].sum()); rings_fr = float(nr[1:].sum())
     b = {}

@@ -21,7 +21,9 @@
 #include <stdint.h>
 #include "velo_gpu.h"
 
-#define VELO_AZ_BINS 512
+#ifndef VELO_AZ_BINS
+#define VELO_AZ_BINS 1024
+#endif
 #define VELO_SECTORS 64
 #define VELO_BINS_PER_SECTOR (VELO_AZ_BINS / VELO_SECTORS)
 #define VELO_MAX_RINGS_HARD 256

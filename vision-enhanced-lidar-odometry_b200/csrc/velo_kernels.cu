@@ -113,10 +113,14 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
         atomicMax(&s_rhi[b / VELO_BINS_PER_SECTOR], rr);
     }
     __syncthreads();
-    // exclusive scan of 512 bins with 256 threads (2 bins each)
-    int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1], total;
-    int ex = block_excl_scan(a0 + a1, s_w, total);
-    s_hist[2 * tid] = ex; s_hist[2 * tid + 1] = ex + a0;
+    // exclusive scan of the AZ bins with 256 threads (AZ/256 consecutive bins each)
+    constexpr int PER = VELO_AZ_BINS / 256;
+    int av[PER], sum = 0, total;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { av[k] = s_hist[PER * tid + k]; sum += av[k]; }
+    int ex = block_excl_scan(sum, s_w, total);
+#pragma unroll
+    for (int k = 0; k < PER; k++) { s_hist[PER * tid + k] = ex; ex += av[k]; }
     __syncthreads();
     int *cs = B.cell_start + ((size_t)slot * B.R + ring) * (VELO_AZ_BINS + 1);
     for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) cs[i] = r0 + s_hist[i];

@@ -121,6 +121,16 @@ int  velo_gpu_calib_from_kitti(const float P[48], const float Tr[12], int img_wi
 int  velo_pixel2canonical(const velo_gpu_calib *calib, int cam, const float *pix, int n, float *canon);
 int  velo_canonical2pixel(const velo_gpu_calib *calib, int cam, const float *canon, int n, float *pix);
 
+/* ---------------------------------------------------------------- KITTI wire formats (host only) */
+/* calib.txt as parsed by kitti.h:66-105: a label token then 12 floats, for P0..P3, then "Tr:" + 12 floats. */
+int  velo_kitti_load_calib(const char *path, float P[48], float Tr[12]);
+/* velodyne/NNNNNN.bin as read by loadPoints (kitti.h:121-152): float {x,y,z,reflectance} records.  Returns the number of
+ * points through *n (at most max_points are stored; *n is the count in the file). */
+int  velo_kitti_load_scan(const char *path, float *xyzr, int max_points, int *n);
+/* one line of results/<seq>.txt as written by output_line (kitti.h:202-216): the first 3 rows of a row-major 4x4 pose,
+ * 12 numbers separated (and followed) by a space, default ostream formatting (%g, 6 significant digits). */
+int  velo_kitti_format_pose(const double T[16], char *buf, int buflen);
+
 int  velo_gpu_create(int device, const velo_gpu_params *params, const velo_gpu_calib *calib, velo_gpu_ctx **out);
 int  velo_gpu_destroy(velo_gpu_ctx *ctx);
 const char *velo_gpu_last_error(const velo_gpu_ctx *ctx); /* ctx may be NULL: message of a failed create */

@@ -87,3 +87,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".hpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in txt and "velo_oracle" not in txt and "libvelo_ref" not in txt, os.path.join(dp, f)
+
+
+def test_kitti_wire_formats(velo, tmp_path):
+    """calib.txt / velodyne .bin / pose line formats of kitti.h:59-152,202-216"""
+    P, Tr, w, h = velo.synth.calib_raw(0)
+    lines = [f"P{c}: " + " ".join(repr(float(x)) for x in P[12 * c: 12 * c + 12]) for c in range(4)]
+    lines.append("Tr: " + " ".join(repr(float(x)) for x in Tr))
+    (tmp_path / "calib.txt").write_text("\n".join(lines) + "\n")
+    P2, Tr2 = velo.api.kitti_load_calib(tmp_path / "calib.txt")
+    assert P2.tobytes() == P.tobytes() and Tr2.tobytes() == Tr.tobytes()
+    raw, n = velo.synth.scan(3)
+    raw[:5000].tofile(tmp_path / "000003.bin")
+    back = velo.api.kitti_load_scan(tmp_path / "000003.bin")
+    assert back.tobytes() == raw[:5000].tobytes()
+    with pytest.raises(velo.api.VeloError):
+        velo.api.kitti_load_scan(tmp_path / "missing.bin")
+    T = np.eye(4); T[0, 3] = 1.5; T[2, 3] = -0.25; T[1, 1] = 0.999999123
+    assert velo.api.kitti_format_pose(T) == "1 0 0 1.5 0 0.999999 0 0 0 0 1 -0.25 "

@@ -80,7 +80,7 @@ assert VIS_BLOCK_DTYPE.itemsize == C.sizeof(VisBlock)
 # functions declared in include/velo_gpu.h; tests check that the library exports every one
 EXPORTS = [
     "velo_gpu_abi_version", "velo_gpu_default_params", "velo_gpu_calib_from_kitti", "velo_pixel2canonical",
-    "velo_canonical2pixel", "velo_gpu_create", "velo_gpu_destroy", "velo_gpu_last_error", "velo_gpu_sync",
+    "velo_canonical2pixel", "velo_kitti_load_calib", "velo_kitti_load_scan", "velo_kitti_format_pose", "velo_gpu_create", "velo_gpu_destroy", "velo_gpu_last_error", "velo_gpu_sync",
     "velo_gpu_device_name", "velo_gpu_host_alloc", "velo_gpu_host_free", "velo_gpu_timer_begin", "velo_gpu_timer_end",
     "velo_gpu_profile_enable", "velo_gpu_profile_reset", "velo_gpu_profile_read", "velo_gpu_kernel_name",
     "velo_gpu_scan_upload", "velo_gpu_scan_upload_rings", "velo_gpu_projection_upload", "velo_gpu_scan_info", "velo_gpu_scan_download", "velo_gpu_project",

@@ -35,6 +35,9 @@ def lib():
     L.velo_gpu_calib_from_kitti.argtypes = [_P, _P, C.c_int, C.c_int, _P]
     L.velo_pixel2canonical.argtypes = [_P, C.c_int, _P, C.c_int, _P]
     L.velo_canonical2pixel.argtypes = [_P, C.c_int, _P, C.c_int, _P]
+    L.velo_kitti_load_calib.argtypes = [C.c_char_p, _P, _P]
+    L.velo_kitti_load_scan.argtypes = [C.c_char_p, _P, C.c_int, C.POINTER(C.c_int)]
+    L.velo_kitti_format_pose.argtypes = [_P, C.c_char_p, C.c_int]
     L.velo_gpu_create.argtypes = [C.c_int, _P, _P, C.POINTER(_P)]
     for fn in ("velo_gpu_destroy", "velo_gpu_sync", "velo_gpu_timer_begin", "velo_gpu_profile_reset"):
         getattr(L, fn).argtypes = [_P]
@@ -103,6 +106,35 @@ def canonical2pixel(cal, cam, can):
     out = np.zeros_like(can)
     lib().velo_canonical2pixel(C.addressof(cal), cam, _ptr(can), len(can), _ptr(out))
     return out
+
+
+def kitti_load_calib(path):
+    """calib.txt (kitti.h:66-105) -> (P[48], Tr[12])"""
+    P = np.zeros(48, np.float32); Tr = np.zeros(12, np.float32)
+    rc = lib().velo_kitti_load_calib(str(path).encode(), _ptr(P), _ptr(Tr))
+    if rc:
+        raise VeloError(rc, f"cannot parse {path}")
+    return P, Tr
+
+
+def kitti_load_scan(path, max_points=200000):
+    """velodyne .bin (kitti.h:121-152) -> float32 [n, 4]"""
+    buf = np.zeros((max_points, 4), np.float32)
+    n = C.c_int()
+    rc = lib().velo_kitti_load_scan(str(path).encode(), _ptr(buf), max_points, C.byref(n))
+    if rc:
+        raise VeloError(rc, f"cannot read {path}")
+    return buf[:n.value]
+
+
+def kitti_format_pose(T):
+    """one line of results/<seq>.txt (kitti.h:202-216) for a 4x4 pose"""
+    T = np.ascontiguousarray(T, np.float64).reshape(16)
+    buf = C.create_string_buffer(512)
+    rc = lib().velo_kitti_format_pose(_ptr(T), buf, 512)
+    if rc:
+        raise VeloError(rc, "format_pose")
+    return buf.value.decode()
 
 
 class PinnedPool:

@@ -120,6 +120,50 @@ extern "C" int velo_canonical2pixel(const velo_gpu_calib *c, int cam, const floa
     return VELO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ KITTI wire formats (host only)
+extern "C" int velo_kitti_load_calib(const char *path, float P[48], float Tr[12]) {      // kitti.h:61-105
+    if (!path || !P || !Tr) return VELO_ERR_INVALID_ARG;
+    FILE *f = fopen(path, "r");
+    if (!f) return VELO_ERR_INVALID_ARG;
+    char label[64];
+    int ok = 1;
+    for (int cam = 0; cam < VELO_MAX_CAMS && ok; cam++) {
+        if (fscanf(f, "%63s", label) != 1) { ok = 0; break; }                              // calib_stream >> P;
+        for (int i = 0; i < 12; i++) if (fscanf(f, "%f", &P[12 * cam + i]) != 1) { ok = 0; break; }
+    }
+    if (ok && fscanf(f, "%63s", label) != 1) ok = 0;                                       // "Tr:"
+    for (int i = 0; i < 12 && ok; i++) if (fscanf(f, "%f", &Tr[i]) != 1) ok = 0;
+    fclose(f);
+    return ok ? VELO_OK : VELO_ERR_INVALID_ARG;
+}
+
+extern "C" int velo_kitti_load_scan(const char *path, float *xyzr, int max_points, int *n) { // kitti.h:121-152
+    if (!path || !n || max_points < 0 || (max_points > 0 && !xyzr)) return VELO_ERR_INVALID_ARG;
+    FILE *f = fopen(path, "rb");
+    if (!f) return VELO_ERR_INVALID_ARG;
+    fseek(f, 0, SEEK_END);
+    const long bytes = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    const long total = bytes / (long)(4 * sizeof(float));                                   // fread(...)/4
+    const long take = total < max_points ? total : max_points;
+    const size_t got = take > 0 ? fread(xyzr, 4 * sizeof(float), (size_t)take, f) : 0;
+    fclose(f);
+    *n = (int)total;
+    if ((long)got != take) return VELO_ERR_INVALID_ARG;
+    return total > max_points ? VELO_ERR_CAPACITY : VELO_OK;
+}
+
+extern "C" int velo_kitti_format_pose(const double T[16], char *buf, int buflen) {         // kitti.h:202-216
+    if (!T || !buf || buflen < 1) return VELO_ERR_INVALID_ARG;
+    int o = 0;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) {
+        const int w = snprintf(buf + o, (size_t)(buflen - o), "%g ", T[4 * i + j]);       // std::ostream default: %g, precision 6
+        if (w < 0 || w >= buflen - o) return VELO_ERR_CAPACITY;
+        o += w;
+    }
+    return VELO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ pose constants (hazard H8)
 namespace {
 struct J3 { double a, v[3]; };

@@ -435,3 +435,39 @@ def test_cpp_dropin_header(velo, oracle, calib, params, tmp_path):
         assert np.array_equal(corr[f], ocorr[f]), f
     neq = np.fromfile(tmp_path / "out_neq.bin", np.float64)
     np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max())
+
+
+def test_random_ragged_ring_clouds(velo, oracle, calib, params, ctx):
+    """random ring-structured clouds installed with scan_upload_rings: empty and 1-point rings, grid-snapped coordinates
+    (exact distance ties, duplicated x, z ties), identity / random poses — projection, association and ICP vs the oracle."""
+    from test_properties import _rings
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        quant = [None, 0.25, 0.05][case % 3]
+        ptsS, rsS = _rings(rng, int(rng.integers(1, 10)), int(rng.integers(0, 70)), quant)
+        ptsM, rsM = _rings(rng, int(rng.integers(1, 6)), int(rng.integers(0, 40)), quant)
+        ctx.scan_upload_rings(0, ptsS, rsS); ctx.scan_upload_rings(1, ptsM, rsM)
+        gp, grs = ctx.scan_download(1)
+        assert gp.tobytes() == ptsM.tobytes() and np.array_equal(grs, rsM)
+        for cam in (0, 1):
+            ctx.project(1, cam)
+            rc, proj, valid = ctx.project_download(1, cam)
+            orc, oproj, ovalid = oracle.project(ptsM, rsM, calib, cam)
+            assert np.array_equal(rc, orc) and proj.tobytes() == oproj.tobytes() and valid.tobytes() == ovalid.tobytes(), case
+            F = int(rng.integers(0, 80))
+            kp = np.stack([rng.uniform(calib.min_x[cam], calib.max_x[cam], F), rng.uniform(calib.min_y[cam], calib.max_y[cam], F)], 1).astype(np.float32)
+            hd, kw = ctx.depth_assoc(1, cam, kp, 0)
+            ohd, okw = oracle.depth_assoc(ovalid, oproj, orc, kp)
+            assert np.array_equal(hd, ohd) and kw.tobytes() == okw.tobytes(), case
+        pose = np.zeros(6) if quant else np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.05, 3)])
+        for it, skip in ((1, 1), (2, 1), (1, 3)):
+            corr, neq, kept = ctx.icp_pass(1, 0, pose, it, skip)
+            ocorr, oneq, okept = oracle.icp_pass(ptsM, rsM, ptsS, rsS, pose, it, skip, params, 0)
+            assert len(corr) == len(ocorr) and kept == okept, case
+            for f in ("src_ring", "src_idx", "kept", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
+                assert np.array_equal(corr[f], ocorr[f]), (case, f)
+            k = ocorr["kept"] == 1
+            assert corr["normal"][k].tobytes() == ocorr["normal"][k].tobytes()
+            np.testing.assert_allclose(corr["residual"][k], ocorr["residual"][k], rtol=RTOL_RES, atol=1e-9)
+            if kept:
+                np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max() + 1e-300)

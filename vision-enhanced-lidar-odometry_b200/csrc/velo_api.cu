@@ -275,6 +275,7 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &B.cell_start, S * R * (VELO_AZ_BINS + 1))); CKC(dalloc(ctx, &B.sec_box, S * R * VELO_SECTORS));
     B.W = (B.R + 63) / 64;
     CKC(dalloc(ctx, &B.mask_lo, S * VELO_SECTORS * VELO_EL_BUCKETS * (size_t)B.W)); CKC(dalloc(ctx, &B.mask_hi, S * VELO_SECTORS * VELO_EL_BUCKETS * (size_t)B.W));
+    CKC(dalloc(ctx, &B.rmask_lo, S * VELO_SECTORS * VELO_RG_BUCKETS * (size_t)B.W)); CKC(dalloc(ctx, &B.rmask_hi, S * VELO_SECTORS * VELO_RG_BUCKETS * (size_t)B.W));
     CKC(dalloc(ctx, &B.proj, S * C * N)); CKC(dalloc(ctx, &B.valid, S * C * N)); CKC(dalloc(ctx, &B.proj_count, S * C * R)); CKC(dalloc(ctx, &B.proj_yrange, S * C * R));
     const size_t SK = S * VELO_NUM_KP_SETS * C;
     CKC(dalloc(ctx, &B.kp, SK * F)); CKC(dalloc(ctx, &B.n_kp, SK)); CKC(dalloc(ctx, &B.has_depth, SK * F)); CKC(dalloc(ctx, &B.kpwd, SK * F));

@@ -48,6 +48,10 @@ __device__ __forceinline__ int el_bucket(float el) {   // monotone non-decreasin
     int b = (int)floorf((el - VELO_EL_MIN) * (VELO_EL_BUCKETS / (VELO_EL_MAX - VELO_EL_MIN)));
     return min(max(b, 0), VELO_EL_BUCKETS - 1);
 }
+__device__ __forceinline__ int rg_bucket(float rho) {   // monotone non-decreasing in rho
+    int b = (int)floorf(log2f(fmaxf(rho, VELO_RG_MIN) * (1.0f / VELO_RG_MIN)) * VELO_RG_PER_OCTAVE);
+    return min(max(b, 0), VELO_RG_BUCKETS - 1);
+}
 __device__ __forceinline__ int az_bin(float az) {
     int b = (int)((az + CUDART_PI_F) * (VELO_AZ_BINS / (2.0f * CUDART_PI_F)));
     return min(max(b, 0), VELO_AZ_BINS - 1);

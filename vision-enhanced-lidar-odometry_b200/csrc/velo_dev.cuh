@@ -11,6 +11,7 @@
 //   cell_start int    [S][R][AZ+1]    start of (ring, azimuth bin) in `sorted` (slot-relative)
 //   sec_box    float4 [S][R][SEC]     {elev lo, elev hi, range min, range max} of the ring inside one azimuth sector
 //   mask_lo/hi u64    [S][SEC][EL][W] cumulative ring bit masks over elevation buckets (W = ceil(R/64) words)
+//   rmask_lo/hi u64   [S][SEC][RG][W] cumulative ring bit masks over log-spaced range buckets
 //   proj       float2 [S][C][N]       canonical projection, ring r at offset ring_start[r] (velo.h:366)
 //   valid      float4 [S][C][N]       matching cam-0 points (velo.h:368)
 //   proj_count int    [S][C][R],  proj_yrange float2 [S][C][R] (y range of the ring's projections, prunes the association)
@@ -30,6 +31,9 @@
 #define VELO_EL_BUCKETS 256         /* elevation buckets of the ring-mask tables */
 #define VELO_EL_MIN (-0.47f)        /* rad; elevations outside [EL_MIN, EL_MAX] clamp to the edge buckets (still conservative) */
 #define VELO_EL_MAX (0.10f)
+#define VELO_RG_BUCKETS 256         /* log-spaced range buckets of the ring-mask tables: 42 per octave from 2 m (1.6 % steps) */
+#define VELO_RG_MIN 2.0f
+#define VELO_RG_PER_OCTAVE 42.0f
 #define VELO_IDX_BITS 20            /* index-in-ring bits of the neighbour key */
 #define VELO_RING_BITS 12
 
@@ -52,7 +56,8 @@ struct DevBuffers {
     int S, N, R, C, F, MM, P;
     float4 *raw; uint32_t *flagbits; int *n_points; int *n_rings; int *ring_start; int *status;
     float4 *pts; float4 *sorted; int *cell_start; float4 *sec_box;
-    unsigned long long *mask_lo, *mask_hi; int W;   // [S][SEC][EL_BUCKETS][W]: rings with bucket(lo) <= b / bucket(hi) >= b
+    unsigned long long *mask_lo, *mask_hi; int W;   // [S][SEC][EL_BUCKETS][W]: rings with bucket(elev lo) <= b / bucket(elev hi) >= b
+    unsigned long long *rmask_lo, *rmask_hi;        // [S][SEC][RG_BUCKETS][W]: the same over log-spaced range buckets
     float2 *proj; float4 *valid; int *proj_count; float2 *proj_yrange;
     float2 *kp; int *n_kp; int *has_depth; float4 *kpwd; int *n_hits; int *hit_tmp; float4 *kpwd_tmp;
     int *matches; int *n_matches;

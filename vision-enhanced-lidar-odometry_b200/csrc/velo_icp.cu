@@ -86,38 +86,28 @@ __device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, cons
     }
     return bi >= 0 ? make_key(bd, s, bi) : KEY_INF;
 }
-// Per-ring pruning from the sector boxes {elev lo, elev hi, range min, range max} of the ring inside the window's sectors.
-// With rq, rp the ranges from the index origin and `angle` the angle between the two directions,
-//     d2(q,p) = (rq - rp)^2 + 4 rq rp sin^2(angle/2),     sin^2(angle/2) = sin^2(de/2) + cos(eq) cos(ep) sin^2(daz/2)   (haversine)
-// so d2 >= dr^2 + 4 rq rlo sin^2(gap/2) =: lb2 and the ring is skipped when lb2 > bound.  (A per-ring narrowing of the
-// azimuth window from the same inequality was measured to cost more instructions than the candidates it saves: distance
-// evaluations are cheap here, control flow is not.)  Every quantity is deflated/inflated so that float error in this pruning math can only keep extra candidates.
-__device__ __forceinline__ bool ring_test(const float4 *__restrict__ sb4, const Window &w, float el, float rho, float bnd) {
-    float elo = CUDART_INF_F, ehi = -CUDART_INF_F, rlo = CUDART_INF_F, rhi = -CUDART_INF_F;
-    int sa = w.b0 / VELO_BINS_PER_SECTOR, sb = w.b1 / VELO_BINS_PER_SECTOR;
-    if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
-    for (int sec = sa;; sec = (sec + 1) & (VELO_SECTORS - 1)) {
-        const float4 e = __ldg(sb4 + sec);
-        elo = fminf(elo, e.x); ehi = fmaxf(ehi, e.y); rlo = fminf(rlo, e.z); rhi = fmaxf(rhi, e.w);
-        if (sec == sb) break;
-    }
-    if (!(elo <= ehi)) return false;                                // no point of the ring in these sectors
-    const float g = fmaxf(fmaxf(elo - el, el - ehi) - 2e-5f, 0.0f);
-    const float dr = fmaxf(fmaxf(rlo - rho, rho - rhi) - 1e-5f * (rho + rhi) - 1e-6f, 0.0f);
-    const float h = fminf(0.5f * g, 1.0f);
-    const float sh = h * (1.0f - h * h * (1.0f / 6.0f));           // <= sin(h) for 0 <= h <= 1
-    const float rr = 4.0f * rho * fmaxf(rlo, 0.0f) * (1.0f - 1e-5f);
-    const float dr2 = dr * dr * (1.0f - 1e-5f);
-    return !((dr2 + rr * sh * sh) * (1.0f - 1e-4f) > bnd);
+// Candidate rings (64-ring word `word`) for a query at elevation el / range rho with search radius b: a ring qualifies in a
+// sector of the window if its elevation interval comes within w.gam of el AND its range interval within b of rho
+// (|q-p| >= |rq-rp| and |q-p| >= rq sin(angle), angle >= elevation gap).  Both tests are two loads from cumulative bucket
+// masks (bucket functions are monotone, windows padded => conservative); no per-ring test is needed afterwards.
+struct MaskQ { int e0, e1, r0, r1; };
+__device__ __forceinline__ MaskQ mask_query(float el, float gam, float rho, float b) {
+    MaskQ q;
+    q.e0 = el_bucket(el - gam); q.e1 = el_bucket(el + gam);
+    const float pad = b * (1.0f + 1e-5f) + 1e-5f * rho + 1e-6f;
+    q.r0 = rg_bucket(rho - pad); q.r1 = rg_bucket(rho + pad);
+    return q;
 }
-// candidate rings (64-ring word `word`) whose elevation interval in a sector of the window can come within w.gam of el
-__device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 *__restrict__ mhi, int W, int word, const Window &w, float el) {
-    const int e0 = el_bucket(el - w.gam), e1 = el_bucket(el + w.gam);
+__device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 *__restrict__ mhi, const u64 *__restrict__ rlo, const u64 *__restrict__ rhi,
+                                         int W, int word, const Window &w, const MaskQ &q, bool use_range) {
     int sa = w.b0 / VELO_BINS_PER_SECTOR, sb = w.b1 / VELO_BINS_PER_SECTOR;
     if (w.full) { sa = 0; sb = VELO_SECTORS - 1; }
     u64 m = 0ull;
     for (int sec = sa;; sec = (sec + 1) & (VELO_SECTORS - 1)) {
-        m |= __ldg(mlo + (sec * VELO_EL_BUCKETS + e1) * W + word) & __ldg(mhi + (sec * VELO_EL_BUCKETS + e0) * W + word);
+        const int base = sec * VELO_EL_BUCKETS;
+        u64 t = __ldg(mlo + (base + q.e1) * W + word) & __ldg(mhi + (base + q.e0) * W + word);
+        if (use_range) t &= __ldg(rlo + (base + q.r1) * W + word) & __ldg(rhi + (base + q.r0) * W + word);
+        m |= t;
         if (sec == sb) break;
     }
     return m;
@@ -163,10 +153,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
     const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
-    const float4 *sbS = B.sec_box + (size_t)U.tgt_slot * B.R * VELO_SECTORS;
     const int W = B.W;
     const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
+    const u64 *rloS = B.rmask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
+    const u64 *rhiS = B.rmask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
 
     for (int qb = q0; qb < q1; qb += ICP_THREADS) {
         const int q = qb + tid;
@@ -245,7 +236,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #pragma unroll
                         for (int word = 0; word < 4; word++) {
                             if (word >= W) break;
-                            u64 m = ring_mask(mloS, mhiS, W, word, ws, el) & ~V[word];
+                            u64 m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, ws, mask_query(el, ws.gam, rho, 0.f), false) & ~V[word];
                             V[word] |= m;
                             while (m && kj == KEY_INF) {
                                 const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1;
@@ -283,15 +274,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                                 lev = started ? lev * 2.0f : (tight ? 8.0f : 0.0065f);
                                 started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
-                            Window wl = w; wl.gam = gcur;
-                            m = ring_mask(mloS, mhiS, W, word, wl, el) & ~V[word];
+                            m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, w, mask_query(el, gcur, rho, sqrtf(bound)), true) & ~V[word];
                             V[word] |= m;
                             continue;
                         }
                         const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
-                        // a ring that already holds the best candidate only needs points that beat its own candidate
-                        const bool own = (ki != KEY_INF) && (s == key_ring(ki));
-                        if (!ring_test(sbS + s * VELO_SECTORS, w, el, rho, own ? key_d2(ki) : bound)) continue;
                         const int *cs = csS + s * (VELO_AZ_BINS + 1);
                         if (!w.wrapped) { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + w.b1 + 1); p1 = 0; e1 = 0; }
                         else { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + w.b1 + 1); }

@@ -142,22 +142,25 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
 // The rings whose elevation interval in that sector can intersect [e0, e1] are a subset of mask_lo[bucket(e1)] & mask_hi[bucket(e0)]
 // (bucket() is monotone), which turns the per-query 64-ring scan into two 8-byte loads per sector.
 __global__ void __launch_bounds__(VELO_EL_BUCKETS) k_index_masks(DevBuffers B, int slot0) {
+    static_assert(VELO_EL_BUCKETS == VELO_RG_BUCKETS, "one thread per bucket of either table");
     const int slot = slot0 + blockIdx.y, sec = blockIdx.x, b = threadIdx.x;
     const int nr = B.n_rings[slot];
     const float4 *se = B.sec_box + (size_t)slot * B.R * VELO_SECTORS + sec;
-    unsigned long long *mlo = B.mask_lo + (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
-    unsigned long long *mhi = B.mask_hi + (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
+    const size_t o = (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
     for (int w = 0; w < B.W; w++) {
-        unsigned long long lo = 0ull, hi = 0ull;
+        unsigned long long lo = 0ull, hi = 0ull, rlo = 0ull, rhi = 0ull;
         const int r1 = min(nr, (w + 1) * 64);
         for (int r = w * 64; r < r1; r++) {
             const float4 e = se[(size_t)r * VELO_SECTORS];
             if (e.x <= e.y) {                                   // sector not empty for this ring
-                if (el_bucket(e.x) <= b) lo |= 1ull << (r & 63);
-                if (el_bucket(e.y) >= b) hi |= 1ull << (r & 63);
+                const unsigned long long bit = 1ull << (r & 63);
+                if (el_bucket(e.x) <= b) lo |= bit;
+                if (el_bucket(e.y) >= b) hi |= bit;
+                if (rg_bucket(e.z) <= b) rlo |= bit;
+                if (rg_bucket(e.w) >= b) rhi |= bit;
             }
         }
-        mlo[w] = lo; mhi[w] = hi;
+        B.mask_lo[o + w] = lo; B.mask_hi[o + w] = hi; B.rmask_lo[o + w] = rlo; B.rmask_hi[o + w] = rhi;
     }
 }
 

@@ -471,3 +471,24 @@ def test_random_ragged_ring_clouds(velo, oracle, calib, params, ctx):
             np.testing.assert_allclose(corr["residual"][k], ocorr["residual"][k], rtol=RTOL_RES, atol=1e-9)
             if kept:
                 np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max() + 1e-300)
+
+
+def test_depth_assoc_projection_larger_than_shared_memory(velo, oracle, calib, ctx):
+    """more in-FOV points than the association kernel stages in shared memory (24 576): the global-memory path"""
+    rng = np.random.default_rng(9)
+    n_rings, L = 48, 900
+    pts = []
+    for s in range(n_rings):
+        az = np.sort(rng.uniform(-0.65, 0.65, L)); r = 12.0 + rng.normal(0, 0.05, L)
+        pts.append(np.stack([r * np.sin(az), np.full(L, -1.9 + 0.08 * s) + rng.normal(0, 0.01, L), r * np.cos(az), np.ones(L)], 1))
+    pts = np.concatenate(pts).astype(np.float32)
+    rs = (np.arange(n_rings + 1) * L).astype(np.int32)
+    ctx.scan_upload_rings(0, pts, rs)
+    ctx.project(0, 0)
+    rc, proj, valid = ctx.project_download(0, 0)
+    orc, oproj, ovalid = oracle.project(pts, rs, calib, 0)
+    assert rc.sum() > 24576 and np.array_equal(rc, orc) and proj.tobytes() == oproj.tobytes()
+    kp = np.stack([rng.uniform(-0.6, 0.6, 3000), rng.uniform(-0.16, 0.16, 3000)], 1).astype(np.float32)
+    hd, kw = ctx.depth_assoc(0, 0, kp, 0)
+    ohd, okw = oracle.depth_assoc(ovalid, oproj, orc, kp)
+    assert np.array_equal(hd, ohd) and kw.tobytes() == okw.tobytes() and (hd >= 0).sum() > 1000

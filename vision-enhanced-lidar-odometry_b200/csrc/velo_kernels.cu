@@ -245,75 +245,132 @@ __device__ __forceinline__ bool width_ok(float dx, const DevCalib &cal) {   // h
     return fabsf(dx) < cal.assoc_thr;
 }
 
-// one thread per keypoint: the ring loop, binary search and bilinear patch of velo.h:390-492, step for step (H4/H5).
-// grid = (keypoint chunks, cameras, slots*sets)
-__global__ void __launch_bounds__(128) k_assoc_search(DevBuffers B, DevCalib cal, int slot0, int set0, int nsets, int cam0) {
+// The ring loop, binary search and bilinear patch of velo.h:390-492, step for step (H4/H5), one thread per keypoint.
+// One CTA per (camera, slot) serves every keypoint set of that image: the projections of all rings (x,y pairs, ~140 KB for a
+// KITTI frame) are first staged in shared memory, because the binary searches are scattered 8-byte reads that would otherwise
+// cost one L1 wavefront per lane.  A projection that does not fit (more than ASSOC_CAP points in the FOV) is searched in
+// global memory through the same code path.
+#define ASSOC_THREADS 512
+#define ASSOC_CAP 24576           /* float2 entries of dynamic shared memory (192 KB) */
+#define ASSOC_YB 256              /* keypoint-y buckets of the needed-ring range table */
+__global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, DevCalib cal, int slot0, int set0, int nsets, int cam0) {
+    extern __shared__ float2 s_proj[];
+    __shared__ int s_off[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_rs[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_cnt[VELO_MAX_RINGS_HARD];
     __shared__ float2 s_yr[VELO_MAX_RINGS_HARD];
-    const int cam = cam0 + blockIdx.y;
-    const int slot = slot0 + blockIdx.z / nsets, set = set0 + blockIdx.z % nsets;
+    const int cam = cam0 + blockIdx.x, slot = slot0 + blockIdx.y;
     const int nr = B.n_rings[slot];
-    const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + set) * B.C + cam;
-    const int F = B.n_kp[sc];
-    if ((int)(blockIdx.x * blockDim.x) >= F) return;
     const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
     const int *pc = B.proj_count + ((size_t)slot * B.C + cam) * B.R;
     const float2 *yr = B.proj_yrange + ((size_t)slot * B.C + cam) * B.R;
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) { s_rs[i] = rs[i]; s_cnt[i] = pc[i]; s_yr[i] = yr[i]; }
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= F) return;
     const float2 *proj = B.proj + ((size_t)slot * B.C + cam) * B.N;
     const float4 *valid = B.valid + ((size_t)slot * B.C + cam) * B.N;
-    const float2 kp = B.kp[sc * B.F + k];
-    int last = -1, hit = 0;
-    float4 out = make_float4(0.f, 0.f, 0.f, 1.0f);
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) { s_rs[i] = rs[i]; s_cnt[i] = pc[i]; s_yr[i] = yr[i]; }
+    __syncthreads();
+    if (threadIdx.x == 0) { int o = 0; for (int s = 0; s < nr; s++) { s_off[s] = o; o += s_cnt[s]; } s_off[nr] = o; }
+    __syncthreads();
+    const bool fits = s_off[nr] <= ASSOC_CAP;
+    if (fits) {
+        for (int s = 0; s < nr; s++) {
+            const float2 *src = proj + s_rs[s];
+            float2 *dst = s_proj + s_off[s];
+            for (int i = threadIdx.x; i < s_cnt[s]; i += blockDim.x) dst[i] = src[i];
+        }
+    }
+    __syncthreads();
+    const float2 *base = fits ? s_proj : proj;
+    const int *off = fits ? s_off : s_rs;
     // A hit on the ring pair (s-1, s) needs (proj[s][mid].y > kp.y) != (proj[s-1][last].y > kp.y) (velo.h:414-415): impossible
     // when both rings lie entirely above (y > kp.y everywhere) or entirely not-above.  A ring whose two pairs are both
-    // impossible cannot influence the result, so its binary search is skipped (its `last` is never consulted).
-    bool ab_prev = true, be_prev = true;             // ring -1: both flags set => pair impossible
-    bool ab_cur = nr > 0 ? (s_yr[0].x > kp.y) : true, be_cur = nr > 0 ? (s_yr[0].y <= kp.y) : true;
-    for (int s = 0; s < nr; s++) {
-        const bool ab_next = (s + 1 < nr) ? (s_yr[s + 1].x > kp.y) : true, be_next = (s + 1 < nr) ? (s_yr[s + 1].y <= kp.y) : true;
-        const bool pair_prev = !((ab_prev && ab_cur) || (be_prev && be_cur));
-        const bool pair_next = !((ab_cur && ab_next) || (be_cur && be_next));
-        ab_prev = ab_cur; be_prev = be_cur; ab_cur = ab_next; be_cur = be_next;
-        if (!pair_prev && !pair_next) { last = -1; continue; }
-        const int cnt = s_cnt[s];
-        if (cnt <= 1) { last = -1; continue; }                       // velo.h:400-403
-        const float2 *ps = proj + s_rs[s];
-        int lo = 0, hi = cnt - 2, mid = 0;
-        bool found = false;
-        while (lo <= hi) {                                           // velo.h:404-412
-            mid = (lo + hi) >> 1;
-            const float2 a = ps[mid];
-            if (a.x > kp.x) { hi = mid - 1; continue; }
-            const float2 b = ps[mid + 1];
-            if (b.x <= kp.x) { lo = mid + 1; continue; }
-            found = true;
-            if (last != -1) {
-                const float2 *pq = proj + s_rs[s - 1];
-                const float2 c = pq[last], d = pq[last + 1];
-                if (((a.y > kp.y) != (c.y > kp.y)) && width_ok(__fsub_rn(a.x, b.x), cal) && width_ok(__fsub_rn(c.x, d.x), cal)) {
-                    const float4 *vs = valid + s_rs[s], *vq = valid + s_rs[s - 1];
-                    float3 i1 = lerp3(vs[mid], vs[mid + 1], a.x, b.x, kp.x);          // velo.h:445-450
-                    float3 i2 = lerp3(vq[last], vq[last + 1], c.x, d.x, kp.x);        // velo.h:451-456
-                    float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                       // velo.h:457-462
-                    float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                       // velo.h:463-468
-                    float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
-                    out = make_float4(r.x, r.y, r.z, 1.0f);
-                    hit = 1;
+    // impossible cannot influence the result, so its binary search is skipped (its `last` is never consulted); skipping a ring
+    // leaves last = -1 exactly as a ring without a bracket would.  s_first/s_last bound the rings that can be needed for a
+    // keypoint whose y falls in one of ASSOC_YB buckets of the image height (conservative: evaluated at both bucket edges).
+    __shared__ unsigned char s_first[ASSOC_YB], s_lastr[ASSOC_YB];
+    const float ymin = cal.fov[cam][2], ymax = cal.fov[cam][3], yscale = ASSOC_YB / (ymax - ymin);
+    for (int bkt = threadIdx.x; bkt < ASSOC_YB; bkt += blockDim.x) {
+        const float y0 = ymin + bkt / yscale - 1e-4f, y1 = ymin + (bkt + 1) / yscale + 1e-4f;   // bucket edges, padded
+        int f = nr, l = -1;
+        for (int s2 = 0; s2 < nr; s2++) {
+            // ring s2 is "surely not needed" for every y in [y0,y1] iff both its pairs are impossible for all such y.
+            // pair (a,b) impossible for all y in the bucket if (ymin_a > y1 && ymin_b > y1) || (ymax_a <= y0 && ymax_b <= y0).
+            auto imp = [&](int a2, int b2) -> bool {
+                if (a2 < 0 || b2 >= nr) return true;
+                return (s_yr[a2].x > y1 && s_yr[b2].x > y1) || (s_yr[a2].y <= y0 && s_yr[b2].y <= y0);
+            };
+            if (!(imp(s2 - 1, s2) && imp(s2, s2 + 1))) { if (s2 < f) f = s2; l = s2; }
+        }
+        s_first[bkt] = (unsigned char)min(f, 255); s_lastr[bkt] = (unsigned char)(l < 0 ? 0 : min(l, 255));
+        if (l < 0) { s_first[bkt] = 1; s_lastr[bkt] = 0; }     // empty range
+    }
+    __syncthreads();
+    for (int si = 0; si < nsets; si++) {
+        const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + (set0 + si)) * B.C + cam;
+        const int F = B.n_kp[sc];
+        for (int k0 = 0; k0 < F; k0 += blockDim.x) {
+            const int k = k0 + threadIdx.x;
+            const bool act = k < F;
+            const float2 kp = act ? B.kp[sc * B.F + k] : make_float2(0.f, 0.f);
+            int last = -1, hit = 0;
+            float4 out = make_float4(0.f, 0.f, 0.f, 1.0f);
+            int s = nr, s_end = -1;
+            if (act) {
+                if (kp.y >= ymin && kp.y < ymax) { const int bkt = min(max((int)((kp.y - ymin) * yscale), 0), ASSOC_YB - 1); s = s_first[bkt]; s_end = s_lastr[bkt]; }
+                else { s = 0; s_end = nr - 1; }                                      // keypoint outside the image: no shortcut
+                if (nr > 255) { s = 0; s_end = nr - 1; }
+            }
+            // warp-synchronous rounds: every lane advances (cheaply) to its next needed ring, then all lanes search together
+            for (;;) {
+                while (s <= s_end) {
+                    const bool ab_p = s > 0 ? (s_yr[s - 1].x > kp.y) : true, be_p = s > 0 ? (s_yr[s - 1].y <= kp.y) : true;
+                    const bool ab_c = s_yr[s].x > kp.y, be_c = s_yr[s].y <= kp.y;
+                    const bool ab_n = (s + 1 < nr) ? (s_yr[s + 1].x > kp.y) : true, be_n = (s + 1 < nr) ? (s_yr[s + 1].y <= kp.y) : true;
+                    const bool pair_prev = !((ab_p && ab_c) || (be_p && be_c)), pair_next = !((ab_c && ab_n) || (be_c && be_n));
+                    if ((pair_prev || pair_next) && s_cnt[s] > 1) break;               // ring s needs its binary search
+                    last = -1; s++;                                                    // skipped ring / velo.h:400-403
+                }
+                const bool work = s <= s_end;
+                if (!__any_sync(FULL, work)) break;
+                if (work) {
+                    const int cnt = s_cnt[s];
+                    const float2 *ps = base + off[s];
+                    int lo = 0, hi = cnt - 2, mid = 0;
+                    bool found = false;
+                    while (lo <= hi) {                                           // velo.h:404-412
+                        mid = (lo + hi) >> 1;
+                        const float2 a = ps[mid];
+                        if (a.x > kp.x) { hi = mid - 1; continue; }
+                        const float2 b = ps[mid + 1];
+                        if (b.x <= kp.x) { lo = mid + 1; continue; }
+                        found = true;
+                        if (last != -1) {
+                            const float2 *pq = base + off[s - 1];
+                            const float2 c = pq[last], d = pq[last + 1];
+                            if (((a.y > kp.y) != (c.y > kp.y)) && width_ok(__fsub_rn(a.x, b.x), cal) && width_ok(__fsub_rn(c.x, d.x), cal)) {
+                                const float4 *vs = valid + s_rs[s], *vq = valid + s_rs[s - 1];
+                                float3 i1 = lerp3(vs[mid], vs[mid + 1], a.x, b.x, kp.x);          // velo.h:445-450
+                                float3 i2 = lerp3(vq[last], vq[last + 1], c.x, d.x, kp.x);        // velo.h:451-456
+                                float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                       // velo.h:457-462
+                                float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                       // velo.h:463-468
+                                float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
+                                out = make_float4(r.x, r.y, r.z, 1.0f);
+                                hit = 1;
+                            }
+                        }
+                        last = mid;                                              // velo.h:483
+                        break;
+                    }
+                    if (!found) last = -1;                                       // velo.h:487-489
+                    s = hit ? nr + 1 : s + 1;                                    // velo.h:490
+                    if (hit) s_end = -1;
                 }
             }
-            last = mid;                                              // velo.h:483
-            break;
+            if (act) {
+                B.hit_tmp[sc * B.F + k] = hit;
+                if (hit) B.kpwd_tmp[sc * B.F + k] = out;
+            }
         }
-        if (!found) last = -1;                                       // velo.h:487-489
-        if (hit) break;                                              // velo.h:490
     }
-    B.hit_tmp[sc * B.F + k] = hit;
-    if (hit) B.kpwd_tmp[sc * B.F + k] = out;
 }
 
 // stable compaction in keypoint order (hazard H13): has_depth[k] = running hit count, kpwd appended (velo.h:479-481)
@@ -359,8 +416,9 @@ void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal,
     PRE(VK_PROJECT); k_project<<<g, PROJ_WARPS * 32, 0, L.stream>>>(B, cal, slot0); POST(VK_PROJECT);
 }
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams) {
-    dim3 g((B.F + 127) / 128, ncams, count * nsets);
-    PRE(VK_ASSOC_SEARCH); k_assoc_search<<<g, 128, 0, L.stream>>>(B, cal, slot0, set0, nsets, cam0); POST(VK_ASSOC_SEARCH);
+    dim3 g(ncams, count);
+    cudaFuncSetAttribute(k_assoc_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ASSOC_CAP * sizeof(float2)));
+    PRE(VK_ASSOC_SEARCH); k_assoc_search<<<g, ASSOC_THREADS, ASSOC_CAP * sizeof(float2), L.stream>>>(B, cal, slot0, set0, nsets, cam0); POST(VK_ASSOC_SEARCH);
     dim3 g2(ncams, count * nsets);
     PRE(VK_ASSOC_COMPACT); k_assoc_compact<<<g2, 256, 0, L.stream>>>(B, slot0, set0, nsets, cam0); POST(VK_ASSOC_COMPACT);
 }

@@ -38,12 +38,6 @@ for it, p in ((1, 0), (2, 3)):
             r = corr[i]
             dj = -1.0
             print('    q', i, 'ring', r['src_ring'], 'idx', r['src_idx'], 'kept', r['kept'], 'si', r['np_s_i'], 'sj', r['np_s_j'], 'seed', seed[i], 'exh', exh[i], 'rings', rings[i], 'mask', mask[i], 'range %.2f' % rng[i], 'pt', pts[i, :3])
-        J = corr['jacobian']
-        print('   seeds: frac without kj after seeds %.3f; median seed d_i %.3f seed d_j %.3f final d_j %.3f' % ((J[:, 1] < 0).mean(), np.median(J[:, 0][J[:, 0] >= 0]), np.median(J[:, 1][J[:, 1] >= 0]), np.median(J[:, 2][J[:, 2] >= 0])))
-        for lo_, hi_ in ((0, 30), (30, 100), (100, 300), (300, 5000)):
-            sel = (exh >= lo_) & (exh < hi_)
-            print('   exh in [%d,%d): frac %.3f  nokj-after-seeds %.2f  seed d_j med %.3f final d_j med %.3f rings %.1f mask %.1f range med %.1f' % (lo_, hi_, sel.mean(), (J[sel, 1] < 0).mean(),
-                  np.median(J[sel, 1][J[sel, 1] >= 0]) if (J[sel, 1] >= 0).any() else -1, np.median(J[sel, 2][J[sel, 2] >= 0]) if (J[sel, 2] >= 0).any() else -1, rings[sel].mean(), mask[sel].mean(), np.median(rng[sel])))
         mid = np.nonzero((exh > 100) & (exh < 200) & near)[0]
         for i in mid[:: max(1, len(mid) // 8)][:8]:
             r = corr[i]

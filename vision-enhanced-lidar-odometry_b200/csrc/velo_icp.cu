@@ -7,9 +7,12 @@
 //     i = the smallest key,        j = the smallest key whose ring differs from ring(i).
 // (d2 as f32 bits orders like the value; ties go to the lower ring, then the lower point index — hazards H9 and the
 // north-star tie rule.)  A min over keys is order independent, so any exhaustive enumeration gives bit-identical
-// indices.  The enumeration is pruned, conservatively, with the ring x azimuth organisation of the scan:
-// a ring can only contain a closer point if its elevation interval comes within asin(b/|q|) of the query and
-// only inside the azimuth window asin(b/|q_xy|), b = current bound on sqrt(d2_j).
+// indices.  The enumeration is pruned, conservatively, with the ring x azimuth organisation of the scan: a ring can only
+// contain a point within b of the query q if, inside the azimuth window asin(b/|q_xy|), its elevation interval comes
+// within asin(b/|q|) of q's elevation and its range interval within b of q's range (both read from cumulative bucket
+// masks, two loads each); b = current bound on sqrt(d2_j), seeded by the previous pass of the same frame pair.
+// Measured design rule (tools/exp_icp.sh, tools/tune_*.sh): distance evaluations are cheap, control flow and extra
+// rounds are not.
 #include "velo_common.cuh"
 
 #ifndef ICP_THREADS

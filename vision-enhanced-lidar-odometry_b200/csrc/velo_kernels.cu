@@ -143,21 +143,29 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
 // (bucket() is monotone), which turns the per-query 64-ring scan into two 8-byte loads per sector.
 __global__ void __launch_bounds__(VELO_EL_BUCKETS) k_index_masks(DevBuffers B, int slot0) {
     static_assert(VELO_EL_BUCKETS == VELO_RG_BUCKETS, "one thread per bucket of either table");
+    __shared__ short s_bk[VELO_MAX_RINGS_HARD][4];      // bucket(elev lo), bucket(elev hi), bucket(range min), bucket(range max); -1 = empty
     const int slot = slot0 + blockIdx.y, sec = blockIdx.x, b = threadIdx.x;
     const int nr = B.n_rings[slot];
     const float4 *se = B.sec_box + (size_t)slot * B.R * VELO_SECTORS + sec;
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        const float4 e = se[(size_t)r * VELO_SECTORS];
+        const bool ok = e.x <= e.y;                         // sector not empty for this ring
+        s_bk[r][0] = ok ? (short)el_bucket(e.x) : (short)-1; s_bk[r][1] = (short)el_bucket(e.y);
+        s_bk[r][2] = (short)rg_bucket(e.z); s_bk[r][3] = (short)rg_bucket(e.w);
+    }
+    __syncthreads();
     const size_t o = (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
     for (int w = 0; w < B.W; w++) {
         unsigned long long lo = 0ull, hi = 0ull, rlo = 0ull, rhi = 0ull;
         const int r1 = min(nr, (w + 1) * 64);
         for (int r = w * 64; r < r1; r++) {
-            const float4 e = se[(size_t)r * VELO_SECTORS];
-            if (e.x <= e.y) {                                   // sector not empty for this ring
+            const int e0 = s_bk[r][0];
+            if (e0 >= 0) {
                 const unsigned long long bit = 1ull << (r & 63);
-                if (el_bucket(e.x) <= b) lo |= bit;
-                if (el_bucket(e.y) >= b) hi |= bit;
-                if (rg_bucket(e.z) <= b) rlo |= bit;
-                if (rg_bucket(e.w) >= b) rhi |= bit;
+                if (e0 <= b) lo |= bit;
+                if (s_bk[r][1] >= b) hi |= bit;
+                if (s_bk[r][2] <= b) rlo |= bit;
+                if (s_bk[r][3] >= b) rhi |= bit;
             }
         }
         B.mask_lo[o + w] = lo; B.mask_hi[o + w] = hi; B.rmask_lo[o + w] = rlo; B.rmask_hi[o + w] = rhi;

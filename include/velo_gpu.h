@@ -195,6 +195,27 @@ int  velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1, int slot2
                                const double pose[6], int iter,
                                velo_vis_block *blocks, int block_capacity, int *n_blocks, double *neq);
 
+/* frameToFrame (velo.h:598-919) with the per-pass ceres::Solve replaced by a device-resident Levenberg-Marquardt solve
+ * (SURVEY.md §8(f1)): for iter = 1..f2f_iterations { freeze the visual blocks at the current transform (velo.h:622-792);
+ * for icp_iter < icp_iterations { freeze the ICP correspondences at the current transform (velo.h:806-894); minimise the
+ * robustified cost of the frozen blocks over the 6-vector } }.  The trust-region policy restates Ceres' defaults; agreement
+ * with a Ceres build is "to solver tolerance" (Ceres is not available here), agreement with the oracle's identical
+ * restatement is tested.  n_matches may be NULL (no visual terms); enable_icp = 0 drops the ICP blocks (main.cpp:43).
+ * transform is in/out, like velo.h:611. */
+#define VELO_MAX_SOLVES 16
+typedef struct velo_f2f_report {
+    int n_solves;
+    int lm_iterations[VELO_MAX_SOLVES];   /* trial evaluations after the initial one */
+    int accepted_steps[VELO_MAX_SOLVES];
+    int reason[VELO_MAX_SOLVES];          /* 1 function tol, 2 gradient tol, 3 parameter tol, 4 radius, 5 no blocks, 6 max iterations */
+    int n_blocks[VELO_MAX_SOLVES];
+    double initial_cost[VELO_MAX_SOLVES], final_cost[VELO_MAX_SOLVES];
+    double pose[VELO_MAX_SOLVES][6];      /* transform after each solve */
+} velo_f2f_report;
+int  velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, int slot_S, int set2,
+                             const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
+                             int enable_icp, int icp_skip, double transform[6], velo_f2f_report *report);
+
 /* ---------------------------------------------------------------- batched path (throughput) */
 /* A batch is `count` consecutive slots starting at slot0.  Inputs are concatenated with fixed strides:
  *   scans   [count][max_points][4] float,   n_points[count]

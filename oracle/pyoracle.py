@@ -66,6 +66,7 @@ class Oracle:
         L.oracle_calib_from_kitti.argtypes = [_P, _P, C.c_int, C.c_int, _P]
         L.oracle_pixel2canonical.argtypes = [_P, C.c_int, _P, C.c_int, _P]
         L.oracle_canonical2pixel.argtypes = [_P, C.c_int, _P, C.c_int, _P]
+        L.oracle_frame_to_frame.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 10 + [C.c_int, C.c_int, _P, _P]
         L.oracle_bench_frames.restype = C.c_double
         L.oracle_bench_frames.argtypes = [C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]
 
@@ -177,6 +178,29 @@ class Oracle:
             nb = _lib.ref_visual(ncam, F, MM, _ptr(kp1), _ptr(kp2), _ptr(hd1), _ptr(hd2), _ptr(kpwd1), _ptr(kpwd2), _ptr(n_matches), _ptr(matches),
                                  _ptr(lm_valid), _ptr(lm_xyz), C.addressof(cal), _ptr(pose), it, _ptr(blocks), cap, _ptr(neq))
         return blocks[:nb], neq
+
+    # ---- f1: frameToFrame with the frozen-block LM solve
+    def frame_to_frame(self, ptsM, rsM, ptsS, rsS, cal, prm, transform, vis=None, enable_icp=1, icp_skip=1):
+        """vis = (kp1, kp2, hd1, hd2, kpwd1, kpwd2, n_matches, matches[C][MM][2]) or None"""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        ptsM, ptsS, rsM, rsS = f32(ptsM), f32(ptsS), i32(rsM), i32(rsS)
+        t = np.ascontiguousarray(transform, np.float64).copy()
+        rep = abi.F2FReport()
+        if vis is not None:
+            kp1, kp2, hd1, hd2, kw1, kw2, nm, mt = vis
+            kp1, kp2, kw1, kw2, hd1, hd2, nm, mt = f32(kp1), f32(kp2), f32(kw1), f32(kw2), i32(hd1), i32(hd2), i32(nm), i32(mt)
+            ncam, F, MM = kp1.shape[0], kp1.shape[1], mt.shape[1]
+            args = [_ptr(kp1), _ptr(kp2), _ptr(hd1), _ptr(hd2), _ptr(kw1), _ptr(kw2), _ptr(nm), _ptr(mt)]
+        else:
+            ncam, F, MM = prm.num_cams, 1, 1
+            args = [None] * 8
+        self.lib.oracle_frame_to_frame(_ptr(ptsM), _ptr(rsM), len(rsM) - 1, _ptr(ptsS), _ptr(rsS), len(rsS) - 1, ncam, F, MM, *args,
+                                       C.addressof(cal), C.addressof(prm), enable_icp, icp_skip, _ptr(t), C.addressof(rep))
+        n = rep.n_solves
+        return t, {"n_solves": n, "lm_iterations": list(rep.lm_iterations)[:n], "accepted_steps": list(rep.accepted_steps)[:n], "reason": list(rep.reason)[:n],
+                   "n_blocks": list(rep.n_blocks)[:n], "initial_cost": list(rep.initial_cost)[:n], "final_cost": list(rep.final_cost)[:n],
+                   "pose": np.array([list(rep.pose[i]) for i in range(n)])}
 
     # ---- timed CPU baseline
     def bench_frames(self, batch, prm, cal, threads, stages=abi.STAGE_ALL, want_out=False):

@@ -492,3 +492,66 @@ def test_depth_assoc_projection_larger_than_shared_memory(velo, oracle, calib, c
     hd, kw = ctx.depth_assoc(0, 0, kp, 0)
     ohd, okw = oracle.depth_assoc(ovalid, oproj, orc, kp)
     assert np.array_equal(hd, ohd) and kw.tobytes() == okw.tobytes() and (hd >= 0).sum() > 1000
+
+
+def test_frame_to_frame_device_solve(velo, oracle, calib, ctx):
+    """SURVEY §8(f1): velo_gpu_frame_to_frame (frozen blocks + device-resident LM in place of ceres::Solve) against the oracle's
+    identical restatement, ICP only and ICP + visual terms, from the reference's initial guess (main.cpp:170).  Tolerance =
+    solver tolerance (function_tolerance 1e-6): the two implementations take the same LM path, sums differ at 1e-13."""
+    prm = ctx.prm
+    rawM, rawS = small_scan(velo, 8, range(8, 56), 2), small_scan(velo, 7, range(8, 56), 2)
+    ctx.scan_upload(1, rawM); ctx.scan_upload(0, rawS)
+    ptsM, rsM, _ = oracle.segment(rawM, calib)
+    ptsS, rsS, _ = oracle.segment(rawS, calib)
+    truth = velo.synth.pose(8)
+    guess = np.array([0, 0, 0, 0, 0, 1.0])
+    skip = 4
+    # ---- ICP only
+    gx, grep = ctx.frame_to_frame(1, 1, 0, 0, guess, enable_icp=1, icp_skip=skip)
+    ox, orep = oracle.frame_to_frame(ptsM, rsM, ptsS, rsS, calib, prm, guess, None, 1, skip)
+    assert grep["n_solves"] == orep["n_solves"] == prm.f2f_iterations * prm.icp_iterations
+    assert grep["n_blocks"] == orep["n_blocks"] and grep["reason"] == orep["reason"]
+    assert grep["lm_iterations"] == orep["lm_iterations"] and grep["accepted_steps"] == orep["accepted_steps"]
+    np.testing.assert_allclose(grep["pose"], orep["pose"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(grep["final_cost"], orep["final_cost"], rtol=1e-8)
+    np.testing.assert_allclose(gx, ox, rtol=0, atol=1e-8)
+    assert np.abs(gx[:3] - truth[:3]).max() < 1e-3 and np.abs(gx[3:] - truth[3:]).max() < 1e-2     # and it recovers the true motion
+    assert grep["final_cost"][0] < grep["initial_cost"][0]
+    # ---- ICP + visual terms (full frameToFrame schedule)
+    F = 800
+    data = {}
+    for slot, f, raw in ((0, 7, rawS), (1, 8, rawM)):
+        pts, rs, _ = oracle.segment(raw, calib)
+        kpA, kpB, m = velo.synth.features(f, F)
+        hd = np.zeros((2, 2, F), np.int32); kw = np.zeros((2, 2, F, 4), np.float32)
+        for cam in (0, 1):
+            ctx.project(slot, cam)
+            rc, proj, valid = oracle.project(pts, rs, calib, cam)
+            for s, kp in enumerate((kpA[cam], kpB[cam])):
+                h, k = oracle.depth_assoc(valid, proj, rc, kp)
+                ctx.depth_assoc(slot, cam, kp, s)
+                hd[s, cam] = h; kw[s, cam, : len(k)] = k
+        data[f] = (kpA, kpB, m, hd, kw)
+    kpA7, _, _, hd7, kw7 = data[7]
+    _, kpB8, m8, hd8, kw8 = data[8]
+    MM = ctx.prm.max_matches
+    matches = np.zeros((2, MM, 2), np.int32); nm = np.zeros(2, np.int32); cat = []
+    for cam in (0, 1):
+        idx = np.nonzero(m8[cam])[0]
+        nm[cam] = len(idx); matches[cam, : len(idx), 0] = idx; matches[cam, : len(idx), 1] = idx
+        cat.append(matches[cam, : len(idx)])
+    Fp = ctx.prm.max_features
+    pad = lambda a, shape: np.concatenate([a, np.zeros((a.shape[0], shape - a.shape[1]) + a.shape[2:], a.dtype)], 1)
+    vis = (pad(kpB8, Fp), pad(kpA7, Fp), pad(hd8[1], Fp), pad(hd7[0], Fp), pad(kw8[1], Fp), pad(kw7[0], Fp), nm, matches)
+    gx, grep = ctx.frame_to_frame(1, 1, 0, 0, guess, n_matches=nm, matches=np.concatenate(cat), enable_icp=1, icp_skip=skip)
+    ox, orep = oracle.frame_to_frame(ptsM, rsM, ptsS, rsS, calib, prm, guess, vis, 1, skip)
+    assert grep["n_blocks"] == orep["n_blocks"] and grep["reason"] == orep["reason"] and grep["lm_iterations"] == orep["lm_iterations"]
+    np.testing.assert_allclose(grep["pose"], orep["pose"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(gx, ox, rtol=0, atol=1e-8)
+    assert grep["n_blocks"][0] > orep["n_blocks"][0] - 1 and max(grep["n_blocks"]) > 8000
+    # ---- visual terms only (the shipped configuration: ENABLE_ICP commented out, main.cpp:43)
+    gx, grep = ctx.frame_to_frame(1, 1, 0, 0, guess, n_matches=nm, matches=np.concatenate(cat), enable_icp=0, icp_skip=skip)
+    ox, orep = oracle.frame_to_frame(ptsM, rsM, ptsS, rsS, calib, prm, guess, vis, 0, skip)
+    assert grep["n_solves"] == orep["n_solves"] == prm.f2f_iterations and grep["n_blocks"] == orep["n_blocks"]
+    np.testing.assert_allclose(gx, ox, rtol=0, atol=1e-7)
+    assert np.abs(gx[3:] - truth[3:]).max() < 0.05

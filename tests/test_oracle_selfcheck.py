@@ -47,3 +47,17 @@ def test_generator_shape(velo, oracle, calib):
     assert 600 < (hd >= 0).sum() < 1800 and m.sum() > 2000
     p = velo.synth.pose(42)
     assert np.abs(p[:3]).max() < 0.05 and 0.7 < p[5] < 1.3
+
+
+def test_oracle_frame_to_frame_recovers_motion(velo, oracle, calib, params):
+    """SURVEY §8(f1) on the CPU side: frozen-block LM (the stand-in for ceres::Solve) inside the reference's 2 x 3 schedule
+    recovers the synthetic ground-truth motion from the reference's initial guess (main.cpp:170) to noise level."""
+    from conftest import small_scan
+    rawM, rawS = small_scan(velo, 8, range(10, 54), 2), small_scan(velo, 7, range(10, 54), 2)
+    ptsM, rsM, _ = oracle.segment(rawM, calib)
+    ptsS, rsS, _ = oracle.segment(rawS, calib)
+    truth = velo.synth.pose(8)
+    x, rep = oracle.frame_to_frame(ptsM, rsM, ptsS, rsS, calib, params, np.array([0, 0, 0, 0, 0, 1.0]), None, 1, 5)
+    assert rep["n_solves"] == 6 and all(r in (1, 2, 3) for r in rep["reason"])
+    assert all(f <= i for f, i in zip(rep["final_cost"], rep["initial_cost"]))
+    assert np.abs(x[:3] - truth[:3]).max() < 1e-3 and np.abs(x[3:] - truth[3:]).max() < 1e-2

@@ -57,6 +57,7 @@ def lib():
     L.velo_gpu_depth_assoc.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]
     L.velo_gpu_icp_pass.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]
     L.velo_gpu_visual_residuals.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
+    L.velo_gpu_frame_to_frame.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]
     L.velo_gpu_batch_upload.argtypes = [_P, C.c_int, C.c_int, _P]
     L.velo_gpu_batch_run.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
     L.velo_gpu_batch_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
@@ -286,6 +287,21 @@ class Context:
         self._ck(self.L.velo_gpu_visual_residuals(self.h, slot1, set1, slot2, set2, _ptr(n_matches), _ptr(matches), _ptr(lm_valid), _ptr(lm_xyz),
                                                   _ptr(pose), it, _ptr(blocks), cap, C.byref(nb), _ptr(neq)))
         return blocks[:nb.value], neq
+
+    def frame_to_frame(self, slot_M, set1, slot_S, set2, transform, n_matches=None, matches=None, enable_icp=1, icp_skip=None, lm_valid=None, lm_xyz=None):
+        """velo.h:598-919 with the device-resident solve; returns (transform[6], report dict)"""
+        t = np.ascontiguousarray(transform, np.float64).copy()
+        nm = None if n_matches is None else np.ascontiguousarray(n_matches, np.int32)
+        mt = None if matches is None else np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+        lv = None if lm_valid is None else np.ascontiguousarray(lm_valid, np.int32)
+        lx = None if lm_xyz is None else np.ascontiguousarray(lm_xyz, np.float32)
+        rep = abi.F2FReport()
+        self._ck(self.L.velo_gpu_frame_to_frame(self.h, slot_M, set1, slot_S, set2, _ptr(nm), _ptr(mt), _ptr(lv), _ptr(lx), enable_icp,
+                                                self.prm.icp_skip if icp_skip is None else icp_skip, _ptr(t), C.addressof(rep)))
+        n = rep.n_solves
+        return t, {"n_solves": n, "lm_iterations": list(rep.lm_iterations)[:n], "accepted_steps": list(rep.accepted_steps)[:n], "reason": list(rep.reason)[:n],
+                   "n_blocks": list(rep.n_blocks)[:n], "initial_cost": list(rep.initial_cost)[:n], "final_cost": list(rep.final_cost)[:n],
+                   "pose": np.array([list(rep.pose[i]) for i in range(n)])}
 
     # ---- batched path
     def batch_upload(self, slot0, batch):

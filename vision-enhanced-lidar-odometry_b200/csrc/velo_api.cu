@@ -31,6 +31,9 @@ struct velo_gpu_ctx {
     velo_icp_corr *d_corr = nullptr;
     VisMatchOut *d_mout = nullptr;
     int *d_lm_valid = nullptr; float4 *d_lm_xyz = nullptr;
+    // device-resident solve
+    LmState *d_lm = nullptr; double *d_pose = nullptr, *d_eval_partial = nullptr, *d_eval_out = nullptr, *d_zero_neq = nullptr;
+    unsigned char *d_sel = nullptr;
     std::vector<int> h_npoints;     // host copy of n_points per slot (single-frame path)
     // timing
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -215,7 +218,7 @@ void make_pose_pack(const double pose[6], PosePack *P) {
 
 // ------------------------------------------------------------------------------------------------ profiling hooks
 static const char *k_names[VELO_NUM_KERNELS] = { "ingest_flags", "ingest_rings", "ingest_permute", "index_build", "project_occlude",
-                                                 "assoc_search", "assoc_compact", "icp_pass", "neq_reduce", "visual_residuals", "index_masks", "misc1" };
+                                                 "assoc_search", "assoc_compact", "icp_pass", "neq_reduce", "visual_residuals", "index_masks", "lm_solve" };
 extern "C" const char *velo_gpu_kernel_name(int k) { return (k >= 0 && k < VELO_NUM_KERNELS) ? k_names[k] : ""; }
 
 static cudaEvent_t get_event(velo_gpu_ctx *c) {
@@ -295,6 +298,8 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &ctx->d_vis_partial, vpart * 64)); CKC(dalloc(ctx, &ctx->d_vis_out, n_vis_units * VELO_NEQ_STRIDE));
     CKC(dalloc(ctx, &ctx->d_corr, N)); CKC(dalloc(ctx, &ctx->d_mout, C * MM));
     CKC(dalloc(ctx, &ctx->d_lm_valid, C * MM)); CKC(dalloc(ctx, &ctx->d_lm_xyz, C * MM));
+    CKC(dalloc(ctx, &ctx->d_lm, 1)); CKC(dalloc(ctx, &ctx->d_pose, 8)); CKC(dalloc(ctx, &ctx->d_eval_partial, (size_t)296 * 64));
+    CKC(dalloc(ctx, &ctx->d_eval_out, VELO_NEQ_STRIDE)); CKC(dalloc(ctx, &ctx->d_zero_neq, VELO_NEQ_STRIDE)); CKC(dalloc(ctx, &ctx->d_sel, C * MM));
     ctx->h_npoints.assign(S, 0);
     // calibration for the device
     DevCalib &d = ctx->dcal; memset(&d, 0, sizeof(d));
@@ -635,6 +640,90 @@ extern "C" int velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1,
     if (blocks && nb > block_capacity) return fail(ctx, VELO_ERR_CAPACITY, "block_capacity too small");
     if (n_blocks) *n_blocks = nb;
     if (neq) memcpy(neq, out, sizeof(out));
+    return VELO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device-resident frameToFrame (f1)
+extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, int slot_S, int set2,
+                                       const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
+                                       int enable_icp, int icp_skip, double transform[6], velo_f2f_report *report) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot_M) || check_slot(ctx, slot_S)) return VELO_ERR_INVALID_ARG;
+    if (!transform || icp_skip < 1 || set1 < 0 || set1 >= VELO_NUM_KP_SETS || set2 < 0 || set2 >= VELO_NUM_KP_SETS) return fail(ctx, VELO_ERR_INVALID_ARG, "bad argument");
+    const int F2F = ctx->prm.f2f_iterations, ICP = enable_icp ? ctx->prm.icp_iterations : 1;
+    if (F2F < 1 || ICP < 1 || F2F * ICP > VELO_MAX_SOLVES) return fail(ctx, VELO_ERR_CAPACITY, "f2f_iterations * icp_iterations exceeds VELO_MAX_SOLVES");
+    CK(cudaSetDevice(ctx->device));
+    int st = slot_status(ctx, slot_M); if (st) return st;
+    st = slot_status(ctx, slot_S); if (st) return st;
+    const DevBuffers &B = ctx->B;
+    const int C = B.C, MM = B.MM;
+    const bool visual = n_matches != nullptr;
+    if (visual) {       // install the match lists (same layout as velo_gpu_visual_residuals)
+        int off = 0, tot = 0;
+        for (int c = 0; c < C; c++) { if (n_matches[c] < 0 || n_matches[c] > MM) return fail(ctx, VELO_ERR_CAPACITY, "more matches than max_matches"); tot += n_matches[c]; }
+        if (tot > 0 && !matches) return fail(ctx, VELO_ERR_INVALID_ARG, "null matches");
+        for (int c = 0; c < C; c++) {
+            if (n_matches[c] > 0) {
+                CK(cudaMemcpyAsync(B.matches + 2 * (((size_t)slot_M * C + c) * MM), matches + 2 * (size_t)off, (size_t)n_matches[c] * 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                if (lm_valid) {
+                    CK(cudaMemcpyAsync(ctx->d_lm_valid + (size_t)c * MM, lm_valid + off, (size_t)n_matches[c] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                    CK(cudaMemcpyAsync(ctx->d_lm_xyz + (size_t)c * MM, lm_xyz + 4 * (size_t)off, (size_t)n_matches[c] * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+                }
+            }
+            off += n_matches[c];
+        }
+        CK(cudaMemcpyAsync(B.n_matches + (size_t)slot_M * C, n_matches, C * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    Launcher L = launcher(ctx);
+    const VisTun tun = vis_tun(ctx);
+    const int *d_lmv = (visual && lm_valid) ? ctx->d_lm_valid : nullptr;
+    const float4 *d_lmx = (visual && lm_valid) ? ctx->d_lm_xyz : nullptr;
+    velo_f2f_report rep; memset(&rep, 0, sizeof(rep));
+    const int eval_ctas = 148, max_lm = 50;
+    for (int iter = 1; iter <= F2F; iter++) {
+        VisUnit *vu = &ctx->h_vis_units[0];
+        if (visual) {   // freeze the visual block list of this f2f iteration at the current transform (velo.h:622-792)
+            memset(vu, 0, sizeof(*vu));
+            vu->slot1 = slot_M; vu->set1 = set1; vu->slot2 = slot_S; vu->set2 = set2; vu->iter = iter;
+            memcpy(vu->pose, transform, 6 * sizeof(double));
+            CK(cudaMemcpyAsync(ctx->d_vis_units, vu, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));     // h_vis_units[0] is rewritten below
+            launch_visual(L, B, ctx->dcal, ctx->d_vis_units, 1, tun, d_lmv, d_lmx, ctx->d_vis_partial, ctx->d_vis_out, nullptr, 32,
+                          VisFixed{ nullptr, ctx->d_sel, nullptr, nullptr });
+        }
+        for (int ii = 0; ii < ICP; ii++) {
+            if (enable_icp) {   // freeze the ICP correspondences at the current transform (velo.h:806-894)
+                init_icp_unit(ctx, &ctx->h_icp_units[0], slot_M, slot_S, icp_skip);
+                add_icp_pass(ctx, &ctx->h_icp_units[0], transform, iter);
+                CK(cudaMemcpyAsync(ctx->d_icp_units, ctx->h_icp_units, sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemsetAsync(ctx->d_corr, 0, (size_t)B.N * sizeof(velo_icp_corr), ctx->stream));
+                launch_icp(L, B, ctx->dcal, ctx->d_icp_units, 1, 1, auto_ctas(ctx, 1, ctx->icp_partial_ctas), ctx->d_icp_partial, ctx->d_icp_out, 1, ctx->d_corr);
+            }
+            CK(cudaMemcpyAsync(ctx->d_pose, transform, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));     // `transform` / h_icp_units are host memory reused below
+            launch_lm_init(L, ctx->d_lm, ctx->d_pose, max_lm);
+            LmState hs; memset(&hs, 0, sizeof(hs));
+            for (int ev = 0; ev <= max_lm && !hs.done; ) {
+                for (int k = 0; k < 4 && ev <= max_lm; k++, ev++) {   // a few controller steps per host look
+                    if (visual)
+                        launch_visual(L, B, ctx->dcal, ctx->d_vis_units, 1, tun, d_lmv, d_lmx, ctx->d_vis_partial, ctx->d_vis_out, nullptr, 32,
+                                      VisFixed{ ctx->d_sel, nullptr, ctx->d_lm->xt_ptr(), ctx->d_lm->done_ptr() });
+                    if (enable_icp)
+                        launch_icp_eval(L, B, ctx->d_corr, B.N, slot_M, ctx->d_lm, ctx->prm.loss_thresh_3DPD, ctx->prm.weight_3DPD, ctx->d_eval_partial, eval_ctas, ctx->d_eval_out);
+                    launch_lm_step(L, ctx->d_lm, enable_icp ? ctx->d_eval_out : ctx->d_zero_neq, visual ? ctx->d_vis_out : ctx->d_zero_neq);
+                }
+                CK(cudaMemcpyAsync(&hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            CK(cudaGetLastError());
+            memcpy(transform, hs.x, 6 * sizeof(double));
+            const int k = rep.n_solves++;
+            rep.lm_iterations[k] = hs.iter; rep.accepted_steps[k] = hs.accepted; rep.reason[k] = hs.reason; rep.n_blocks[k] = hs.n_blocks;
+            rep.initial_cost[k] = hs.init_cost; rep.final_cost[k] = hs.cost;
+            memcpy(rep.pose[k], hs.x, 6 * sizeof(double));
+        }
+    }
+    if (report) *report = rep;
     return VELO_OK;
 }
 

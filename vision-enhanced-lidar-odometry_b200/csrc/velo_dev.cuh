@@ -39,7 +39,7 @@
 
 enum {
     VK_INGEST_FLAGS = 0, VK_INGEST_RINGS, VK_INGEST_PERMUTE, VK_INDEX_BUILD, VK_PROJECT, VK_ASSOC_SEARCH,
-    VK_ASSOC_COMPACT, VK_ICP_PASS, VK_NEQ_REDUCE, VK_VISUAL, VK_INDEX_MASKS, VK_MISC1
+    VK_ASSOC_COMPACT, VK_ICP_PASS, VK_NEQ_REDUCE, VK_VISUAL, VK_INDEX_MASKS, VK_SOLVE
 };
 
 // calibration packed for kernel parameters
@@ -103,8 +103,23 @@ struct VisTun {
     int en2d2d, en3d2d, abs_trunc, pad;
 };
 
+// fixed-block-list mode of the visual kernel (device-resident solve): frozen type masks per (camera, match), pose read from
+// device memory, convergence flag of the solver.  All members may be null.
+struct VisFixed { const unsigned char *sel_in; unsigned char *sel_out; const double *pose; const int *done; };
+
 // per-match parity record of the visual kernel: up to 3 blocks
 struct VisMatchOut { int n; int pad; velo_vis_block b[3]; };
+
+// state of the device-resident Levenberg-Marquardt solve (velo_solve.cu); lives in device memory
+struct LmState {
+    double x[6], xt[6], delta[6];     // accepted pose, trial pose, last step
+    double H[21], g[6];               // robustified normal equations at x
+    double cost, init_cost, model_change, radius, decrease_factor;
+    double function_tolerance, gradient_tolerance, parameter_tolerance;
+    int iter, done, phase, reason, accepted, max_iterations, n_blocks, pad;
+    __host__ __device__ const double *xt_ptr() const { return xt; }
+    __host__ __device__ const int *done_ptr() const { return &done; }
+};
 
 struct Launcher {
     cudaStream_t stream;
@@ -123,4 +138,10 @@ void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, i
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
                 double *partial, double *out, int out_stride_passes, velo_icp_corr *corr);
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
-                   const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas);
+                   const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas,
+                   VisFixed fx = VisFixed{ nullptr, nullptr, nullptr, nullptr });
+
+void launch_lm_init(const Launcher &L, LmState *S, const double *d_pose, int max_iterations);
+void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, int cap, int src_slot, const LmState *S,
+                     double loss_a, double weight, double *partial, int ctas, double *out);
+void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const double *e_vis);

@@ -1,0 +1,180 @@
+// velo_solve.cu — device-resident replacement of the per-pass ceres::Solve of frameToFrame (velo.h:897-902):
+// the residual blocks are frozen (the visual selection of the current f2f iteration + the ICP correspondences of the current
+// ICP pass, exactly what AddResidualBlock had put into the problem), every Levenberg-Marquardt iterate re-evaluates them at
+// the trial pose on the GPU (k_icp_eval_fixed + k_visual in fixed mode), and a one-thread controller kernel does the
+// 6x6 damped solve, the step acceptance and the trust-region update in device memory, so a whole solve is a stream of
+// launches with no host round trip until its result is read.
+//
+// The trust-region policy restates Ceres' documented defaults [recall; Ceres is not in /root/reference, parity for this row is
+// "to solver tolerance" and defined by oracle/velo_oracle.cpp's identical restatement]: Levenberg-Marquardt,
+// initial_trust_region_radius 1e4, min/max_lm_diagonal 1e-6/1e32, min_relative_decrease 1e-3,
+// radius /= max(1/3, 1-(2 rho-1)^3) on success, radius /= 2,4,8.. on failure, function/gradient/parameter tolerances
+// 1e-6 / 1e-10 / 1e-8, max_num_iterations 50.
+#include "velo_jet.cuh"
+
+// ------------------------------------------------------------------------------------------------ fixed 3DPD blocks
+// one thread per correspondence record of the last ICP pass (kept == 1 => a cost3DPD block with p, n, o frozen)
+__global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo_icp_corr *__restrict__ corr, int cap, int src_slot,
+                                                        const double *__restrict__ pose, const int *__restrict__ done,
+                                                        double loss_a, double weight, double *__restrict__ partial) {
+    __shared__ double s_rows[8][32 * NEQ_ROW];
+    __shared__ double s_red[8 * 56];
+    __shared__ int s_cnt;
+    if (done && *done) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const int *rs = B.ring_start + (size_t)src_slot * (B.R + 1);
+    const float4 *pts = B.pts + (size_t)src_slot * B.N;
+    DJ x[6];
+    for (int i = 0; i < 6; i++) { x[i] = dj(pose[i]); x[i].v[i] = 1.0; }
+    double acc = 0.0, raw = 0.0;
+    int nk = 0;
+    const int per = (((cap + gridDim.x - 1) / gridDim.x) + 31) & ~31;
+    const int q0 = blockIdx.x * per, q1 = min(cap, q0 + per);
+    for (int qb = q0; qb < q1; qb += blockDim.x) {
+        const int q = qb + tid;
+        bool kept = false;
+        double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
+        if (q < q1) {
+            const velo_icp_corr c = corr[q];
+            if (c.kept == 1) {
+                const float4 p = pts[rs[c.src_ring] + c.src_idx];
+                const double k[9] = { p.x, p.y, p.z, c.normal[0], c.normal[1], c.normal[2], c.v0[0], c.v0[1], c.v0[2] };
+                DJ r[1];
+                f3dpd(k, x, r);
+                res = r[0].a;
+                for (int i = 0; i < 6; i++) J[i] = r[0].v[i];
+                const double bb = loss_a * loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;   // Scaled(Cauchy), velo.h:885-891
+                rho1 = weight * fmax(2.2250738585072014e-308, inv);
+                rho0h = 0.5 * weight * bb * log(sum);
+                kept = true; nk++;
+            }
+        }
+        warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
+    }
+    for (int o = 16; o > 0; o >>= 1) nk += __shfl_down_sync(FULL, nk, o);
+    if (lane == 0 && nk) atomicAdd(&s_cnt, nk);
+    double *pout = partial + (size_t)blockIdx.x * 64;
+    block_neq_finish(s_red, acc, raw, pout);
+    if (tid == 0) { pout[56] = (double)s_cnt; pout[57] = (double)s_cnt; pout[58] = 0.0; }
+}
+
+__global__ void k_eval_reduce(const double *__restrict__ partial, int ctas, double *__restrict__ out, const int *__restrict__ done) {
+    if (done && *done) return;
+    const int t = threadIdx.x;
+    if (t >= VELO_NEQ_STRIDE) return;
+    double s = 0.0;
+    if (t < 59) for (int c = 0; c < ctas; c++) s += partial[(size_t)c * 64 + t];
+    out[t] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ LM controller
+__device__ bool chol6_solve(const double *A /*21 upper*/, const double *b, double *xo) {
+    double M[6][6], L[6][6];
+    int o = 0;
+    for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++, o++) { M[i][j] = A[o]; M[j][i] = A[o]; }
+    for (int i = 0; i < 6; i++) for (int j = 0; j <= i; j++) {
+        double s = M[i][j];
+        for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+        if (i == j) { if (!(s > 0.0)) return false; L[i][i] = sqrt(s); }
+        else L[i][j] = s / L[j][j];
+    }
+    double y[6];
+    for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+    for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[k][i] * xo[k]; xo[i] = s / L[i][i]; }
+    return true;
+}
+__device__ void sym6_mul(const double *H, const double *v, double *o) {
+    double M[6][6]; int k = 0;
+    for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++, k++) { M[i][j] = H[k]; M[j][i] = H[k]; }
+    for (int i = 0; i < 6; i++) { double s = 0.0; for (int j = 0; j < 6; j++) s += M[i][j] * v[j]; o[i] = s; }
+}
+// propose the next trial step from (H, g, radius); returns false when the damped system is not usable
+__device__ bool lm_propose(LmState *S) {
+    double A[21], mg[6];
+    int o = 0;
+    for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++, o++) {
+        A[o] = S->H[o];
+        if (i == j) A[o] += fmin(fmax(S->H[o], 1e-6), 1e32) / S->radius;           // LevenbergMarquardtStrategy: diag clamp / radius
+    }
+    for (int i = 0; i < 6; i++) mg[i] = -S->g[i];
+    if (!chol6_solve(A, mg, S->delta)) return false;
+    double Hd[6]; sym6_mul(S->H, S->delta, Hd);
+    double mc = 0.0;
+    for (int i = 0; i < 6; i++) mc -= S->delta[i] * (S->g[i] + 0.5 * Hd[i]);       // model_cost_change
+    S->model_change = mc;
+    if (!(mc > 0.0)) return false;
+    double nd = 0.0, nx = 0.0;
+    for (int i = 0; i < 6; i++) { nd += S->delta[i] * S->delta[i]; nx += S->x[i] * S->x[i]; S->xt[i] = S->x[i] + S->delta[i]; }
+    if (sqrt(nd) <= S->parameter_tolerance * (sqrt(nx) + S->parameter_tolerance)) { S->done = 1; S->reason = 3; }
+    return true;
+}
+
+__global__ void k_lm_init(LmState *S, const double *pose, int max_iterations) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int i = 0; i < 6; i++) { S->x[i] = pose[i]; S->xt[i] = pose[i]; S->delta[i] = 0.0; }
+    S->radius = 1e4; S->decrease_factor = 2.0; S->cost = 0.0; S->init_cost = 0.0; S->model_change = 0.0;
+    S->function_tolerance = 1e-6; S->gradient_tolerance = 1e-10; S->parameter_tolerance = 1e-8;
+    S->iter = 0; S->done = 0; S->phase = 0; S->reason = 0; S->accepted = 0; S->max_iterations = max_iterations; S->n_blocks = 0;
+}
+
+// one controller step: consumes the evaluation at the trial pose (sum of the ICP and the visual normal equations)
+__global__ void k_lm_step(LmState *S, const double *__restrict__ e_icp, const double *__restrict__ e_vis) {
+    if (threadIdx.x || blockIdx.x || S->done) return;
+    double H[21], g[6];
+    for (int i = 0; i < 21; i++) H[i] = e_icp[i] + e_vis[i];
+    for (int i = 0; i < 6; i++) g[i] = e_icp[21 + i] + e_vis[21 + i];
+    const double cost = e_icp[27] + e_vis[27];
+    bool take = false;
+    if (S->phase == 0) {                                   // evaluation at the starting point
+        S->phase = 1; S->init_cost = cost; S->n_blocks = (int)(e_icp[56] + e_vis[56]);
+        take = true;
+        if (S->n_blocks == 0) { S->cost = cost; S->done = 1; S->reason = 5; return; }
+    } else {
+        S->iter++;
+        const double rho = (S->cost - cost) / S->model_change;
+        if (rho > 1e-3) {                                  // successful step
+            take = true; S->accepted++;
+            for (int i = 0; i < 6; i++) S->x[i] = S->xt[i];
+            if (fabs(S->cost - cost) < S->function_tolerance * S->cost) { S->done = 1; S->reason = 1; }
+            const double t = 2.0 * rho - 1.0;
+            S->radius = fmin(1e16, S->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+            S->decrease_factor = 2.0;
+        } else {                                           // rejected: shrink the trust region
+            S->radius /= S->decrease_factor; S->decrease_factor *= 2.0;
+            if (S->radius < 1e-32) { S->done = 1; S->reason = 4; }
+        }
+    }
+    if (take) {
+        S->cost = cost;
+        for (int i = 0; i < 21; i++) S->H[i] = H[i];
+        double gmax = 0.0;
+        for (int i = 0; i < 6; i++) { S->g[i] = g[i]; gmax = fmax(gmax, fabs(g[i])); }
+        if (gmax <= S->gradient_tolerance) { S->done = 1; S->reason = 2; }
+    }
+    if (!S->done && S->iter >= S->max_iterations) { S->done = 1; S->reason = 6; }
+    // next trial point (retry with smaller radii while the damped system is unusable)
+    while (!S->done && !lm_propose(S)) {
+        S->radius /= S->decrease_factor; S->decrease_factor *= 2.0;
+        if (S->radius < 1e-32) { S->done = 1; S->reason = 4; }
+    }
+}
+
+void launch_lm_init(const Launcher &L, LmState *S, const double *d_pose, int max_iterations) {
+    if (L.pre) L.pre(L.user, VK_SOLVE);
+    k_lm_init<<<1, 32, 0, L.stream>>>(S, d_pose, max_iterations);
+    if (L.post) L.post(L.user, VK_SOLVE);
+}
+void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, int cap, int src_slot, const LmState *S,
+                     double loss_a, double weight, double *partial, int ctas, double *out) {
+    if (L.pre) L.pre(L.user, VK_SOLVE);
+    k_icp_eval_fixed<<<ctas, 256, 0, L.stream>>>(B, corr, cap, src_slot, S->xt_ptr(), S->done_ptr(), loss_a, weight, partial);
+    k_eval_reduce<<<1, 64, 0, L.stream>>>(partial, ctas, out, S->done_ptr());
+    if (L.post) L.post(L.user, VK_SOLVE);
+}
+void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const double *e_vis) {
+    if (L.pre) L.pre(L.user, VK_SOLVE);
+    k_lm_step<<<1, 32, 0, L.stream>>>(S, e_icp, e_vis);
+    if (L.post) L.post(L.user, VK_SOLVE);
+}

@@ -216,6 +216,14 @@ int  velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, int slot_S
                              const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
                              int enable_icp, int icp_skip, double transform[6], velo_f2f_report *report);
 
+/* matchFeatures (velo.h:499-550): brute-force Hamming 1-NN of every query descriptor among the train
+ * descriptors (cv::BFMatcher(NORM_HAMMING)::match / cv::cuda::DescriptorMatcher, velo.h:517-531; ties -> lower train index),
+ * then the reference's filter: keep (query, train) unless distance > max(1.5 * min_distance, match_thresh) (velo.h:536-548).
+ * Descriptors are desc_bytes (multiple of 8, <= 64; FREAK = 64) bytes per row.  pairs: capacity n_query x 2 ints.
+ * best_idx / best_dist (nullable, n_query each) receive the unfiltered 1-NN. */
+int  velo_gpu_match_hamming(velo_gpu_ctx *ctx, const uint8_t *query, int n_query, const uint8_t *train, int n_train, int desc_bytes,
+                            double match_thresh, int *pairs, int *n_pairs, int *best_idx, int *best_dist);
+
 /* ---------------------------------------------------------------- batched path (throughput) */
 /* A batch is `count` consecutive slots starting at slot0.  Inputs are concatenated with fixed strides:
  *   scans   [count][max_points][4] float,   n_points[count]

@@ -67,6 +67,7 @@ class Oracle:
         L.oracle_pixel2canonical.argtypes = [_P, C.c_int, _P, C.c_int, _P]
         L.oracle_canonical2pixel.argtypes = [_P, C.c_int, _P, C.c_int, _P]
         L.oracle_frame_to_frame.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 10 + [C.c_int, C.c_int, _P, _P]
+        L.oracle_match_hamming.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, _P, _P]
         L.oracle_bench_frames.restype = C.c_double
         L.oracle_bench_frames.argtypes = [C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]
 
@@ -179,6 +180,15 @@ class Oracle:
                                  _ptr(lm_valid), _ptr(lm_xyz), C.addressof(cal), _ptr(pose), it, _ptr(blocks), cap, _ptr(neq))
         return blocks[:nb], neq
 
+    # ---- f4: matchFeatures
+    def match_hamming(self, query, train, match_thresh=29.0):
+        query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)
+        nq, nt = len(query), len(train)
+        db = query.shape[1] if nq else 64
+        pairs = np.zeros((max(nq, 1), 2), np.int32); bi = np.zeros(max(nq, 1), np.int32); bd = np.zeros(max(nq, 1), np.int32)
+        n = self.lib.oracle_match_hamming(_ptr(query), nq, _ptr(train), nt, db, match_thresh, _ptr(pairs), _ptr(bi), _ptr(bd))
+        return pairs[:n], bi[:nq], bd[:nq]
+
     # ---- f1: frameToFrame with the frozen-block LM solve
     def frame_to_frame(self, ptsM, rsM, ptsS, rsS, cal, prm, transform, vis=None, enable_icp=1, icp_skip=1):
         """vis = (kp1, kp2, hd1, hd2, kpwd1, kpwd2, n_matches, matches[C][MM][2]) or None"""
@@ -231,6 +241,7 @@ class Ref:
         L.ref_icp_pass.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, _P]
         L.ref_visual.argtypes = [C.c_int, C.c_int, C.c_int] + [_P] * 10 + [_P, _P, C.c_int, _P, C.c_int, _P]
         L.ref_constants.argtypes = [_P]
+        L.ref_match_hamming.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, _P]
 
     def segment(self, xyzr, cal, max_rings=4096):
         xyzr = np.ascontiguousarray(xyzr, np.float32)
@@ -283,6 +294,13 @@ class Ref:
 
     def visual(self, oracle, *a, **kw):
         return Oracle.visual(oracle, *a, _lib=self.lib, _fn="ref_visual", **kw)
+
+    def match_hamming(self, query, train):
+        query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)
+        nq = len(query)
+        pairs = np.zeros((max(nq, 1), 2), np.int32)
+        n = self.lib.ref_match_hamming(_ptr(query), nq, _ptr(train), len(train), query.shape[1] if nq else 64, _ptr(pairs))
+        return pairs[:n]
 
     def constants(self):
         out = np.zeros(32)

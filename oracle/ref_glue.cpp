@@ -11,6 +11,7 @@
  *     ref_velo_enum       velo.h:3-8          ResidualType
  *     ref_velo_project    velo.h:329-375      projectLidarToCamera
  *     ref_velo_assoc      velo.h:377-497      featureDepthAssociation
+ *     ref_velo_match      velo.h:499-550      matchFeatures (brute-force Hamming + min-distance filter)
  *     ref_velo_visual     velo.h:622-792      frameToFrame, visual residual assembly (loop body of one iter)
  *     ref_velo_icp_a/b    velo.h:806-874 / 875-894   frameToFrame, ICP correspondence + cost3DPD blocks
  * plus costfunctions.h included whole.  Third-party types come from ref_shim/velo_ref_shim.hpp.
@@ -39,6 +40,7 @@ std::vector<double> min_x, max_x, min_y, max_y;
 #include "ref_velo_enum.inc"
 #include "ref_velo_project.inc"
 #include "ref_velo_assoc.inc"
+#include "ref_velo_match.inc"
 
 typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
 
@@ -264,6 +266,17 @@ int ref_visual(int ncam, int F, int MM, const float *kp1, const float *kp2, cons
         }
     }
     return (int)b;
+}
+
+/* matchFeatures (velo.h:499-550) on two descriptor matrices; pairs capacity nq x 2 */
+int ref_match_hamming(const unsigned char *q, int nq, const unsigned char *t, int nt, int bytes, int *pairs) {
+    std::vector<std::vector<cv::Mat>> descriptors(1, std::vector<cv::Mat>(2));
+    descriptors[0][0].rows = nq; descriptors[0][0].cols = bytes; descriptors[0][0].data.assign(q, q + (size_t)nq * bytes);
+    descriptors[0][1].rows = nt; descriptors[0][1].cols = bytes; descriptors[0][1].data.assign(t, t + (size_t)nt * bytes);
+    std::vector<std::pair<int, int>> matches;
+    matchFeatures(descriptors, 0, 0, 0, 1, matches);
+    for (size_t i = 0; i < matches.size(); i++) { pairs[2 * i] = matches[i].first; pairs[2 * i + 1] = matches[i].second; }
+    return (int)matches.size();
 }
 
 /* tunables as compiled from kitti.h:3-35, so tests can assert the defaults of velo_gpu_default_params */

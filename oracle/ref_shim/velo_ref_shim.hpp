@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <cmath>
 #include <cstdlib>
+#include <ctime>
+#include <algorithm>
 #include <iostream>
 #include <fstream>
 #include <iomanip>
@@ -52,6 +54,28 @@ template <class T> struct aligned_allocator : std::allocator<T> {};
 /* ------------------------------------------------------------------ OpenCV */
 namespace cv {
 struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float a, float b) : x(a), y(b) {} };
+/* descriptor matrix: one row per keypoint, `cols` bytes per row (CV_8U) */
+struct Mat { int rows = 0, cols = 0; std::vector<unsigned char> data; };
+struct DMatch { int queryIdx, trainIdx; float distance; };
+enum { NORM_HAMMING = 6 };
+/* cv::BFMatcher(NORM_HAMMING)::match: for every query row the train row with the smallest Hamming distance; the first
+ * (lowest index) minimum wins [recall: batchDistance keeps strict improvements only] */
+struct BFMatcher {
+    explicit BFMatcher(int) {}
+    void match(const Mat &q, const Mat &t, std::vector<DMatch> &out) const {
+        out.clear();
+        if (t.rows == 0) return;
+        for (int i = 0; i < q.rows; i++) {
+            int best = -1, bd = 1 << 30;
+            for (int j = 0; j < t.rows; j++) {
+                int d = 0;
+                for (int k = 0; k < q.cols; k++) d += __builtin_popcount((unsigned)(q.data[(size_t)i * q.cols + k] ^ t.data[(size_t)j * t.cols + k]));
+                if (d < bd) { bd = d; best = j; }
+            }
+            out.push_back(DMatch{ i, best, (float)bd });
+        }
+    }
+};
 } // namespace cv
 
 /* ------------------------------------------------------------------ PCL */

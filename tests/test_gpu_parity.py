@@ -555,3 +555,23 @@ def test_frame_to_frame_device_solve(velo, oracle, calib, ctx):
     assert grep["n_solves"] == orep["n_solves"] == prm.f2f_iterations and grep["n_blocks"] == orep["n_blocks"]
     np.testing.assert_allclose(gx, ox, rtol=0, atol=1e-7)
     assert np.abs(gx[3:] - truth[3:]).max() < 0.05
+
+
+def test_match_hamming_bit_exact(velo, oracle, ctx):
+    """matchFeatures (velo.h:499-550) — brute-force Hamming 1-NN + min-distance filter, integer exact, ties -> lower index"""
+    from test_oracle_vs_ref import _descriptors
+    rng = np.random.default_rng(11)
+    q = _descriptors(rng, 3000)
+    t = np.concatenate([_descriptors(rng, 1800, q[:1800], flips=14), q[7:12], q[7:12], _descriptors(rng, 1200)])
+    t = t[rng.permutation(len(t))]
+    for qq, tt in ((q, t), (q[:1], t), (q, t[:1]), (q[:0], t), (q, t[:0]), (q[:129], t[:257])):
+        gp, gi, gd = ctx.match_hamming(qq, tt)
+        op, oi, od = oracle.match_hamming(qq, tt)
+        assert np.array_equal(gp, op)
+        if len(tt):
+            assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    gp, gi, gd = ctx.match_hamming(q, t)
+    assert 1500 < len(gp) < 3000
+    gp16, _, _ = ctx.match_hamming(q[:, :16].copy(), t[:, :16].copy())          # shorter descriptors (desc_bytes = 16)
+    op16, _, _ = oracle.match_hamming(q[:, :16].copy(), t[:, :16].copy())
+    assert np.array_equal(gp16, op16)

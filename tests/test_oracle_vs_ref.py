@@ -185,3 +185,25 @@ def test_visual_blocks_match_reference(velo, oracle, ref, calib, params, frames,
         assert bo["residual"].tobytes() == br["residual"].tobytes()
         assert bo["jacobian"].tobytes() == br["jacobian"].tobytes()
         np.testing.assert_allclose(neq_o[:58], neq_r[:58], rtol=1e-12, atol=1e-300)
+
+
+def _descriptors(rng, n, base=None, flips=0):
+    d = rng.integers(0, 256, size=(n, 64), dtype=np.uint8) if base is None else base.copy()
+    if base is not None:
+        for i in range(n):
+            for b in rng.integers(0, 512, flips):
+                d[i, b // 8] ^= np.uint8(1 << (b % 8))
+    return d
+
+
+def test_match_hamming_matches_reference(oracle, ref):
+    """velo.h:499-550 verbatim (BFMatcher stand-in: lowest index wins ties) vs the oracle: 64-byte FREAK-sized descriptors,
+    a train set made of noisy copies (real matches), duplicates (ties) and clutter"""
+    rng = np.random.default_rng(3)
+    q = _descriptors(rng, 200)
+    t = np.concatenate([_descriptors(rng, 120, q[:120], flips=12), q[5:9], q[5:9], _descriptors(rng, 150)])
+    for tt in (t, t[:1], t[rng.permutation(len(t))]):
+        po, bi, bd = oracle.match_hamming(q, tt)
+        pr = ref.match_hamming(q, tt)
+        assert np.array_equal(po, pr)
+    assert len(po) > 50 and len(po) < 200

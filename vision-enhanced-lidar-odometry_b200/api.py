@@ -58,6 +58,7 @@ def lib():
     L.velo_gpu_icp_pass.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]
     L.velo_gpu_visual_residuals.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
     L.velo_gpu_frame_to_frame.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]
+    L.velo_gpu_match_hamming.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, C.POINTER(C.c_int), _P, _P]
     L.velo_gpu_batch_upload.argtypes = [_P, C.c_int, C.c_int, _P]
     L.velo_gpu_batch_run.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
     L.velo_gpu_batch_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
@@ -302,6 +303,17 @@ class Context:
         return t, {"n_solves": n, "lm_iterations": list(rep.lm_iterations)[:n], "accepted_steps": list(rep.accepted_steps)[:n], "reason": list(rep.reason)[:n],
                    "n_blocks": list(rep.n_blocks)[:n], "initial_cost": list(rep.initial_cost)[:n], "final_cost": list(rep.final_cost)[:n],
                    "pose": np.array([list(rep.pose[i]) for i in range(n)])}
+
+    def match_hamming(self, query, train, match_thresh=29.0):
+        """matchFeatures (velo.h:499-550): uint8 [n, desc_bytes] descriptors -> (pairs [m, 2], best_idx, best_dist)"""
+        query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)
+        nq, nt = len(query), len(train)
+        db = query.shape[1] if nq else (train.shape[1] if nt else 64)
+        pairs = np.zeros((max(nq, 1), 2), np.int32); bi = np.zeros(max(nq, 1), np.int32); bd = np.zeros(max(nq, 1), np.int32)
+        n = C.c_int()
+        self._ck(self.L.velo_gpu_match_hamming(self.h, _ptr(query) if nq else None, nq, _ptr(train) if nt else None, nt, db, match_thresh,
+                                               _ptr(pairs), C.byref(n), _ptr(bi), _ptr(bd)))
+        return pairs[:n.value], bi[:nq], bd[:nq]
 
     # ---- batched path
     def batch_upload(self, slot0, batch):

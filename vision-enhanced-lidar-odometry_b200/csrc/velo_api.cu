@@ -34,6 +34,8 @@ struct velo_gpu_ctx {
     // device-resident solve
     LmState *d_lm = nullptr; double *d_pose = nullptr, *d_eval_partial = nullptr, *d_eval_out = nullptr, *d_zero_neq = nullptr;
     unsigned char *d_sel = nullptr;
+    // Hamming matcher scratch (grown on demand)
+    unsigned long long *d_hq = nullptr, *d_ht = nullptr; int *d_hidx = nullptr, *d_hdist = nullptr; size_t ham_cap_q = 0, ham_cap_t = 0;
     std::vector<int> h_npoints;     // host copy of n_points per slot (single-frame path)
     // timing
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -321,6 +323,8 @@ extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->d_hq) { cudaFree(ctx->d_hq); cudaFree(ctx->d_hidx); cudaFree(ctx->d_hdist); }
+    if (ctx->d_ht) cudaFree(ctx->d_ht);
     if (ctx->h_icp_units) cudaFreeHost(ctx->h_icp_units);
     if (ctx->h_vis_units) cudaFreeHost(ctx->h_vis_units);
     for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -724,6 +728,47 @@ extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, 
         }
     }
     if (report) *report = rep;
+    return VELO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Hamming matcher (f4)
+extern "C" int velo_gpu_match_hamming(velo_gpu_ctx *ctx, const uint8_t *query, int n_query, const uint8_t *train, int n_train, int desc_bytes,
+                                      double match_thresh, int *pairs, int *n_pairs, int *best_idx, int *best_dist) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (n_query < 0 || n_train < 0 || desc_bytes < 8 || desc_bytes > 64 || (desc_bytes % 8) || !n_pairs || (n_query > 0 && (!query || !pairs)) || (n_train > 0 && !train))
+        return fail(ctx, VELO_ERR_INVALID_ARG, "bad descriptor arguments (desc_bytes must be a multiple of 8, at most 64)");
+    CK(cudaSetDevice(ctx->device));
+    *n_pairs = 0;
+    if (n_query == 0) return VELO_OK;
+    const int words = desc_bytes / 8;
+    const size_t qb = (size_t)n_query * desc_bytes, tb = (size_t)n_train * desc_bytes;
+    if (qb > ctx->ham_cap_q) {
+        if (ctx->d_hq) { cudaFree(ctx->d_hq); cudaFree(ctx->d_hidx); cudaFree(ctx->d_hdist); }
+        CK(cudaMalloc((void **)&ctx->d_hq, qb)); CK(cudaMalloc((void **)&ctx->d_hidx, n_query * sizeof(int))); CK(cudaMalloc((void **)&ctx->d_hdist, n_query * sizeof(int)));
+        ctx->ham_cap_q = qb;
+    }
+    if (tb > ctx->ham_cap_t) { if (ctx->d_ht) cudaFree(ctx->d_ht); CK(cudaMalloc((void **)&ctx->d_ht, tb ? tb : 8)); ctx->ham_cap_t = tb; }
+    CK(cudaMemcpyAsync(ctx->d_hq, query, qb, cudaMemcpyHostToDevice, ctx->stream));
+    if (tb) CK(cudaMemcpyAsync(ctx->d_ht, train, tb, cudaMemcpyHostToDevice, ctx->stream));
+    launch_hamming(launcher(ctx), ctx->d_hq, n_query, ctx->d_ht, n_train, words, ctx->d_hidx, ctx->d_hdist);
+    CK(cudaGetLastError());
+    std::vector<int> idx(n_query), dist(n_query);
+    CK(cudaMemcpyAsync(idx.data(), ctx->d_hidx, n_query * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist.data(), ctx->d_hdist, n_query * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (best_idx) memcpy(best_idx, idx.data(), n_query * sizeof(int));
+    if (best_dist) memcpy(best_dist, dist.data(), n_query * sizeof(int));
+    if (n_train == 0) return VELO_OK;                      // BFMatcher returns no matches for an empty train set
+    // velo.h:536-548: DMatch::distance is a float; the comparison promotes to double
+    double min_dist = 1e9;
+    for (int i = 0; i < n_query; i++) if ((double)(float)dist[i] < min_dist) min_dist = (double)(float)dist[i];
+    const double lim = (1.5 * min_dist > match_thresh) ? 1.5 * min_dist : match_thresh;
+    int n = 0;
+    for (int i = 0; i < n_query; i++) {
+        if ((double)(float)dist[i] > lim) continue;
+        pairs[2 * n] = i; pairs[2 * n + 1] = idx[i]; n++;
+    }
+    *n_pairs = n;
     return VELO_OK;
 }
 

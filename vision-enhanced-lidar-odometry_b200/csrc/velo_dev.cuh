@@ -145,3 +145,4 @@ void launch_lm_init(const Launcher &L, LmState *S, const double *d_pose, int max
 void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, int cap, int src_slot, const LmState *S,
                      double loss_a, double weight, double *partial, int ctas, double *out);
 void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const double *e_vis);
+void launch_hamming(const Launcher &L, const unsigned long long *q, int nq, const unsigned long long *t, int nt, int words, int *best_idx, int *best_dist);

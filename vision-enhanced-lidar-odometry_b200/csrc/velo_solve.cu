@@ -178,3 +178,38 @@ void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const do
     k_lm_step<<<1, 32, 0, L.stream>>>(S, e_icp, e_vis);
     if (L.post) L.post(L.user, VK_SOLVE);
 }
+
+// ------------------------------------------------------------------------------------------------ f4: Hamming matcher
+// velo.h:517-531: for every query descriptor the train descriptor with the smallest Hamming distance (ties -> lower index).
+// One thread per query, descriptor in registers; the train descriptors stream through shared memory in tiles that every
+// thread of the CTA reads as broadcasts.  Integer work, bit-exact.
+#define HAM_THREADS 128
+#define HAM_TILE 128
+__global__ void __launch_bounds__(HAM_THREADS) k_hamming_nn(const unsigned long long *__restrict__ q, int nq, const unsigned long long *__restrict__ t, int nt,
+                                                            int words, int *__restrict__ best_idx, int *__restrict__ best_dist) {
+    __shared__ unsigned long long s_t[HAM_TILE * 8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long d[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) d[w] = (i < nq && w < words) ? q[(size_t)i * words + w] : 0ull;
+    int bi = -1, bd = 0x7fffffff;
+    for (int t0 = 0; t0 < nt; t0 += HAM_TILE) {
+        const int n = min(HAM_TILE, nt - t0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n * words; k += blockDim.x) s_t[(k / words) * 8 + (k % words)] = t[(size_t)t0 * words + k];
+        __syncthreads();
+        for (int j = 0; j < n; j++) {
+            int dist = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) if (w < words) dist += __popcll(d[w] ^ s_t[j * 8 + w]);
+            if (dist < bd) { bd = dist; bi = t0 + j; }
+        }
+    }
+    if (i < nq) { best_idx[i] = bi; best_dist[i] = bd; }
+}
+void launch_hamming(const Launcher &L, const unsigned long long *q, int nq, const unsigned long long *t, int nt, int words, int *best_idx, int *best_dist) {
+    if (nq <= 0) return;
+    if (L.pre) L.pre(L.user, VK_SOLVE);
+    k_hamming_nn<<<(nq + HAM_THREADS - 1) / HAM_THREADS, HAM_THREADS, 0, L.stream>>>(q, nq, t, nt, words, best_idx, best_dist);
+    if (L.post) L.post(L.user, VK_SOLVE);
+}

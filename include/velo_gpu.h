@@ -216,6 +216,18 @@ int  velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, int slot_S
                              const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
                              int enable_icp, int icp_skip, double transform[6], velo_f2f_report *report);
 
+/* triangulatePoint (velo.h:1027-1130) for n_landmarks at once: each landmark is a 3-parameter problem
+ * over its 3-D observations (triangulation3D, TrivialLoss) and 2-D observations (triangulation2D, Scaled(Cauchy)), listed in
+ * the order the reference adds them (camera-major, frame ascending) in CSR form (off3/off2 have n_landmarks+1 entries).
+ * camera_poses: n_frames x 6 (angle-axis, translation; velo.h:1030).  has_init/init_xyz (nullable) = `initial_guess` + `point`;
+ * without an initial guess the start is (0,0,10) and the first 3-D observation alone initialises (velo.h:1041,1082-1085).
+ * out_xyz: n_landmarks x 3 floats (velo.h:1127-1129); iterations (nullable): LM trial evaluations per landmark. */
+typedef struct velo_tri_obs3 { int32_t frame; float x, y, z; } velo_tri_obs3;
+typedef struct velo_tri_obs2 { int32_t frame, cam; float x, y; } velo_tri_obs2;
+int  velo_gpu_triangulate(velo_gpu_ctx *ctx, int n_landmarks, const int *off3, const velo_tri_obs3 *obs3,
+                          const int *off2, const velo_tri_obs2 *obs2, const double *camera_poses, int n_frames,
+                          const float *init_xyz, const int *has_init, float *out_xyz, int *iterations);
+
 /* matchFeatures (velo.h:499-550): brute-force Hamming 1-NN of every query descriptor among the train
  * descriptors (cv::BFMatcher(NORM_HAMMING)::match / cv::cuda::DescriptorMatcher, velo.h:517-531; ties -> lower train index),
  * then the reference's filter: keep (query, train) unless distance > max(1.5 * min_distance, match_thresh) (velo.h:536-548).

@@ -30,6 +30,7 @@ SLICES = {
     "ref_velo_project.inc": ("velo.h", 329, 375, "void projectLidarToCamera(", "}"),
     "ref_velo_assoc.inc": ("velo.h", 377, 497, "std::vector<int> featureDepthAssociation(", "}"),
     "ref_velo_match.inc": ("velo.h", 499, 550, "void matchFeatures(", "}"),
+    "ref_velo_triangulate.inc": ("velo.h", 1027, 1130, "void triangulatePoint(", "}"),
     "ref_velo_visual.inc": ("velo.h", 622, 792, "for(int cam = 0; cam<num_cams; cam++) {", "}"),
     "ref_velo_icp_a.inc": ("velo.h", 806, 874, "for(int sm = 0; sm < scans_M.size() * enable_icp; sm++) {", "N /= N.norm();"),
     "ref_velo_icp_b.inc": ("velo.h", 875, 894, "ceres::CostFunction* cost_function =", "}"),

@@ -68,6 +68,7 @@ class Oracle:
         L.oracle_canonical2pixel.argtypes = [_P, C.c_int, _P, C.c_int, _P]
         L.oracle_frame_to_frame.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int] + [_P] * 10 + [C.c_int, C.c_int, _P, _P]
         L.oracle_match_hamming.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, _P, _P]
+        L.oracle_triangulate.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P]
         L.oracle_bench_frames.restype = C.c_double
         L.oracle_bench_frames.argtypes = [C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]
 
@@ -180,6 +181,22 @@ class Oracle:
                                  _ptr(lm_valid), _ptr(lm_xyz), C.addressof(cal), _ptr(pose), it, _ptr(blocks), cap, _ptr(neq))
         return blocks[:nb], neq
 
+    # ---- f3: triangulatePoint
+    def triangulate(self, off3, obs3, off2, obs2, poses, cal, prm, init_xyz=None, has_init=None, _ref=None, ncam=2):
+        off3 = np.ascontiguousarray(off3, np.int32); off2 = np.ascontiguousarray(off2, np.int32)
+        obs3 = np.ascontiguousarray(obs3, abi.TRI_OBS3_DTYPE); obs2 = np.ascontiguousarray(obs2, abi.TRI_OBS2_DTYPE)
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)
+        n = len(off3) - 1
+        out = np.zeros((max(n, 1), 3), np.float32); it = np.zeros(max(n, 1), np.int32)
+        ini = None if init_xyz is None else np.ascontiguousarray(init_xyz, np.float32)
+        has = None if has_init is None else np.ascontiguousarray(has_init, np.int32)
+        if _ref is None:
+            self.lib.oracle_triangulate(n, _ptr(off3), _ptr(obs3), _ptr(off2), _ptr(obs2), _ptr(poses), len(poses), C.addressof(cal), C.addressof(prm),
+                                        _ptr(ini), _ptr(has), _ptr(out), _ptr(it))
+        else:
+            _ref.ref_triangulate(n, _ptr(off3), _ptr(obs3), _ptr(off2), _ptr(obs2), _ptr(poses), len(poses), C.addressof(cal), ncam, _ptr(ini), _ptr(has), _ptr(out))
+        return out[:n], it[:n]
+
     # ---- f4: matchFeatures
     def match_hamming(self, query, train, match_thresh=29.0):
         query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)
@@ -242,6 +259,7 @@ class Ref:
         L.ref_visual.argtypes = [C.c_int, C.c_int, C.c_int] + [_P] * 10 + [_P, _P, C.c_int, _P, C.c_int, _P]
         L.ref_constants.argtypes = [_P]
         L.ref_match_hamming.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, _P]
+        L.ref_triangulate.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P]
 
     def segment(self, xyzr, cal, max_rings=4096):
         xyzr = np.ascontiguousarray(xyzr, np.float32)

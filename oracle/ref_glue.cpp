@@ -12,6 +12,7 @@
  *     ref_velo_project    velo.h:329-375      projectLidarToCamera
  *     ref_velo_assoc      velo.h:377-497      featureDepthAssociation
  *     ref_velo_match      velo.h:499-550      matchFeatures (brute-force Hamming + min-distance filter)
+ *     ref_velo_triangulate velo.h:1027-1130   triangulatePoint (block assembly; ceres::Solve = the LM stand-in of the shim)
  *     ref_velo_visual     velo.h:622-792      frameToFrame, visual residual assembly (loop body of one iter)
  *     ref_velo_icp_a/b    velo.h:806-874 / 875-894   frameToFrame, ICP correspondence + cost3DPD blocks
  * plus costfunctions.h included whole.  Third-party types come from ref_shim/velo_ref_shim.hpp.
@@ -41,6 +42,10 @@ std::vector<double> min_x, max_x, min_y, max_y;
 #include "ref_velo_project.inc"
 #include "ref_velo_assoc.inc"
 #include "ref_velo_match.inc"
+static int g_num_cams = 2;
+#define num_cams g_num_cams
+#include "ref_velo_triangulate.inc"
+#undef num_cams
 
 typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
 
@@ -76,7 +81,7 @@ static void neq_add(double *neq, const double *r, const double *J, int nr, const
     neq[27] += 0.5 * rho[0]; neq[28 + 27] += 0.5 * s; neq[56] += 1; neq[57] += nr;
 }
 
-static int g_icp_skip = 200, g_num_cams = 2;
+static int g_icp_skip = 200;
 
 extern "C" {
 
@@ -277,6 +282,28 @@ int ref_match_hamming(const unsigned char *q, int nq, const unsigned char *t, in
     matchFeatures(descriptors, 0, 0, 0, 1, matches);
     for (size_t i = 0; i < matches.size(); i++) { pairs[2 * i] = matches[i].first; pairs[2 * i + 1] = matches[i].second; }
     return (int)matches.size();
+}
+
+/* triangulatePoint (velo.h:1027-1130) per landmark, CSR observations as in velo_gpu_triangulate */
+int ref_triangulate(int n, const int *off3, const velo_tri_obs3 *obs3, const int *off2, const velo_tri_obs2 *obs2, const double *poses, int n_frames,
+                    const velo_gpu_calib *cal, int ncam, const float *init_xyz, const int *has_init, float *out_xyz) {
+    set_calib(cal);
+    g_num_cams = ncam;
+    std::vector<double[6]> camera_poses(n_frames);
+    for (int f = 0; f < n_frames; f++) for (int i = 0; i < 6; i++) camera_poses[f][i] = poses[6 * f + i];
+    for (int l = 0; l < n; l++) {
+        /* the reference keys 3-D observations by camera too; the functor ignores the camera, so camera 0 carries them all in order */
+        std::vector<std::map<int, cv::Point2f>> keypoint_obs2(ncam);
+        std::vector<std::map<int, pcl::PointXYZ>> keypoint_obs3(ncam);
+        for (int k = off3[l]; k < off3[l + 1]; k++) keypoint_obs3[0][obs3[k].frame] = pcl::PointXYZ(obs3[k].x, obs3[k].y, obs3[k].z);
+        for (int k = off2[l]; k < off2[l + 1]; k++) keypoint_obs2[obs2[k].cam][obs2[k].frame] = cv::Point2f(obs2[k].x, obs2[k].y);
+        pcl::PointXYZ point;
+        const bool ig = has_init && has_init[l];
+        if (ig) point = pcl::PointXYZ(init_xyz[3 * l], init_xyz[3 * l + 1], init_xyz[3 * l + 2]);
+        triangulatePoint(keypoint_obs2, keypoint_obs3, camera_poses, point, ig);
+        out_xyz[3 * l] = point.x; out_xyz[3 * l + 1] = point.y; out_xyz[3 * l + 2] = point.z;
+    }
+    return 0;
 }
 
 /* tunables as compiled from kitti.h:3-35, so tests can assert the defaults of velo_gpu_default_params */

@@ -188,12 +188,14 @@ template <typename T> inline void AngleAxisRotatePoint(const T angle_axis[3], co
 struct CostFunction {
     virtual ~CostFunction() {}
     virtual int num_residuals() const = 0;
-    virtual void Evaluate6(const double *x, double *r, double *J) const = 0; /* J row-major nres x 6 */
+    virtual int num_params() const = 0;
+    virtual void Evaluate6(const double *x, double *r, double *J) const = 0; /* J row-major nres x num_params */
 };
 template <class F, int M, int NP> struct AutoDiffCostFunction : CostFunction {
     std::unique_ptr<F> f;
     explicit AutoDiffCostFunction(F *fn) : f(fn) {}
     int num_residuals() const override { return M; }
+    int num_params() const override { return NP; }
     void Evaluate6(const double *x, double *r, double *J) const override {
         Jet<NP> xj[NP], rj[M];
         for (int i = 0; i < NP; i++) { xj[i] = Jet<NP>(x[i]); xj[i].v[i] = 1.0; }
@@ -220,6 +222,9 @@ struct CauchyLoss : LossFunction {
         rho[0] = b_ * log(sum); rho[1] = std::max(std::numeric_limits<double>::min(), inv); rho[2] = -c_ * (inv * inv);
     }
 };
+struct TrivialLoss : LossFunction {
+    void Evaluate(double s, double rho[3]) const override { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+};
 struct ScaledLoss : LossFunction {
     std::unique_ptr<LossFunction> rho_; double a_;
     ScaledLoss(LossFunction *rho, double a, Ownership) : rho_(rho), a_(a) {}
@@ -238,4 +243,84 @@ struct Problem {
     }
     void RemoveResidualBlock(ResidualBlockId id) { blocks[id].alive = false; }
 };
+
+/* ceres::Solve stand-in for problems with ONE parameter block of n <= 6 doubles: Levenberg-Marquardt trust region with Ceres'
+ * documented defaults [recall] (initial radius 1e4, min/max_lm_diagonal 1e-6/1e32, min_relative_decrease 1e-3, radius update
+ * 1/max(1/3, 1-(2rho-1)^3), halving with doubling factor on failure, function/gradient/parameter tolerance 1e-6/1e-10/1e-8,
+ * 50 iterations).  Third-party behaviour: parity with a real Ceres build is "to solver tolerance". */
+enum LinearSolverType { DENSE_QR, DENSE_SCHUR };
+struct Solver { struct Options { LinearSolverType linear_solver_type = DENSE_QR; bool minimizer_progress_to_stdout = false; int num_threads = 1; };
+                struct Summary { int iterations = 0; double initial_cost = 0, final_cost = 0; }; };
+inline void Solve(const Solver::Options &, Problem *problem, Solver::Summary *summary) {
+    int n = 0; double *x = nullptr;
+    for (auto &b : problem->blocks) if (b.alive) { n = b.cost->num_params(); x = b.x; break; }
+    if (!x) return;
+    const int T = n * (n + 1) / 2;
+    auto eval = [&](const double *xx, double &cost, double *H, double *g) {
+        cost = 0; for (int i = 0; i < T; i++) H[i] = 0; for (int i = 0; i < n; i++) g[i] = 0;
+        for (auto &b : problem->blocks) {
+            if (!b.alive) continue;
+            double r[8], J[48], rho[3]; const int nr = b.cost->num_residuals();
+            b.cost->Evaluate6(xx, r, J);
+            double s = 0; for (int i = 0; i < nr; i++) s += r[i] * r[i];
+            b.loss->Evaluate(s, rho);
+            int o = 0;
+            for (int a = 0; a < n; a++) for (int c = a; c < n; c++, o++) { double h = 0; for (int i = 0; i < nr; i++) h += J[n * i + a] * J[n * i + c]; H[o] += rho[1] * h; }
+            for (int a = 0; a < n; a++) { double t = 0; for (int i = 0; i < nr; i++) t += J[n * i + a] * r[i]; g[a] += rho[1] * t; }
+            cost += 0.5 * rho[0];
+        }
+    };
+    auto chol = [&](const double *A, const double *b, double *xo) -> bool {
+        double M[6][6], L[6][6]; int o = 0;
+        for (int i = 0; i < n; i++) for (int j = i; j < n; j++, o++) { M[i][j] = A[o]; M[j][i] = A[o]; }
+        for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) {
+            double s = M[i][j]; for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+            if (i == j) { if (!(s > 0.0)) return false; L[i][i] = std::sqrt(s); } else L[i][j] = s / L[j][j];
+        }
+        double y[6];
+        for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+        for (int i = n - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < n; k++) s -= L[k][i] * xo[k]; xo[i] = s / L[i][i]; }
+        return true;
+    };
+    double cost, H[21], g[6], c2, H2[21], g2[6], xt[6], delta[6], radius = 1e4, dec = 2.0, mc = 0;
+    bool done = false; int iter = 0;
+    eval(x, cost, H, g);
+    summary->initial_cost = cost;
+    auto gsmall = [&]() { double m = 0; for (int i = 0; i < n; i++) m = std::max(m, std::fabs(g[i])); return m <= 1e-10; };
+    auto propose = [&]() -> bool {
+        double A[21], mg[6]; int o = 0;
+        for (int i = 0; i < n; i++) for (int j = i; j < n; j++, o++) { A[o] = H[o]; if (i == j) A[o] += std::min(std::max(H[o], 1e-6), 1e32) / radius; }
+        for (int i = 0; i < n; i++) mg[i] = -g[i];
+        if (!chol(A, mg, delta)) return false;
+        double M[6][6]; int k = 0;
+        for (int i = 0; i < n; i++) for (int j = i; j < n; j++, k++) { M[i][j] = H[k]; M[j][i] = H[k]; }
+        mc = 0;
+        for (int i = 0; i < n; i++) { double hd = 0; for (int j = 0; j < n; j++) hd += M[i][j] * delta[j]; mc -= delta[i] * (g[i] + 0.5 * hd); }
+        if (!(mc > 0.0)) return false;
+        double nd = 0, nx = 0;
+        for (int i = 0; i < n; i++) { nd += delta[i] * delta[i]; nx += x[i] * x[i]; xt[i] = x[i] + delta[i]; }
+        if (std::sqrt(nd) <= 1e-8 * (std::sqrt(nx) + 1e-8)) done = true;
+        return true;
+    };
+    auto next_trial = [&]() {
+        if (!done && iter >= 50) done = true;
+        while (!done && !propose()) { radius /= dec; dec *= 2.0; if (radius < 1e-32) done = true; }
+    };
+    if (gsmall()) done = true;
+    next_trial();
+    while (!done) {
+        eval(xt, c2, H2, g2); iter++;
+        const double rho = (cost - c2) / mc;
+        if (rho > 1e-3) {
+            for (int i = 0; i < n; i++) x[i] = xt[i];
+            if (std::fabs(cost - c2) < 1e-6 * cost) done = true;
+            const double t = 2.0 * rho - 1.0;
+            radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - t * t * t)); dec = 2.0;
+            cost = c2; for (int i = 0; i < T; i++) H[i] = H2[i]; for (int i = 0; i < n; i++) g[i] = g2[i];
+            if (gsmall()) done = true;
+        } else { radius /= dec; dec *= 2.0; if (radius < 1e-32) done = true; }
+        next_trial();
+    }
+    summary->iterations = iter; summary->final_cost = cost;
+}
 } // namespace ceres

@@ -575,3 +575,23 @@ def test_match_hamming_bit_exact(velo, oracle, ctx):
     gp16, _, _ = ctx.match_hamming(q[:, :16].copy(), t[:, :16].copy())          # shorter descriptors (desc_bytes = 16)
     op16, _, _ = oracle.match_hamming(q[:, :16].copy(), t[:, :16].copy())
     assert np.array_equal(gp16, op16)
+
+
+def test_batched_triangulation(velo, oracle, calib, params, ctx):
+    """velo_gpu_triangulate (one thread per landmark, LM on 3 parameters) vs the oracle's restatement of
+    triangulatePoint (velo.h:1027-1130); "to solver tolerance" (function_tolerance 1e-6) on the float outputs."""
+    import tri_data
+    off3, obs3, off2, obs2, poses, truth = tri_data.make(5, L=4000, n_frames=8)
+    g, git = ctx.triangulate(off3, obs3, off2, obs2, poses)
+    o, oit = oracle.triangulate(off3, obs3, off2, obs2, poses, calib, params)
+    np.testing.assert_allclose(g, o, rtol=2e-6, atol=2e-6)
+    assert (git == oit).mean() > 0.999
+    n3, n2 = np.diff(off3), np.diff(off2)
+    good = (n3 >= 1) & (n2 >= 3)
+    assert good.sum() > 500 and np.abs(g[good] - truth[good]).max() < 0.3
+    init = (truth + 0.3).astype(np.float32); has = (np.arange(len(truth)) % 2).astype(np.int32)
+    g2, _ = ctx.triangulate(off3, obs3, off2, obs2, poses, init, has)
+    o2, _ = oracle.triangulate(off3, obs3, off2, obs2, poses, calib, params, init, has)
+    np.testing.assert_allclose(g2, o2, rtol=2e-6, atol=2e-6)
+    e, _ = ctx.triangulate(np.zeros(1, np.int32), obs3[:0], np.zeros(1, np.int32), obs2[:0], poses)
+    assert len(e) == 0

@@ -207,3 +207,22 @@ def test_match_hamming_matches_reference(oracle, ref):
         pr = ref.match_hamming(q, tt)
         assert np.array_equal(po, pr)
     assert len(po) > 50 and len(po) < 200
+
+
+def test_triangulation_matches_reference(velo, oracle, ref, calib, params):
+    """SURVEY §8(f3): triangulatePoint (velo.h:1027-1130) compiled verbatim (ceres::Solve = the LM stand-in) vs the oracle,
+    with and without initial guesses; landmarks with no, only 2-D, only 3-D and mixed observations"""
+    import tri_data
+    off3, obs3, off2, obs2, poses, truth = tri_data.make(1)
+    a, it = oracle.triangulate(off3, obs3, off2, obs2, poses, calib, params)
+    b, _ = oracle.triangulate(off3, obs3, off2, obs2, poses, calib, params, _ref=ref.lib)
+    np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6)
+    n3, n2 = np.diff(off3), np.diff(off2)
+    good = (n3 >= 1) & (n2 >= 3)
+    assert good.sum() > 50 and np.abs(a[good] - truth[good]).max() < 0.25          # and it triangulates
+    none = (n3 == 0) & (n2 == 0)
+    assert none.any() and np.all(a[none] == [0, 0, 10])                            # untouched start (velo.h:1041)
+    init = (truth + 0.3).astype(np.float32); has = (np.arange(len(truth)) % 2).astype(np.int32)
+    a2, _ = oracle.triangulate(off3, obs3, off2, obs2, poses, calib, params, init, has)
+    b2, _ = oracle.triangulate(off3, obs3, off2, obs2, poses, calib, params, init, has, _ref=ref.lib)
+    np.testing.assert_allclose(a2, b2, rtol=1e-6, atol=1e-6)

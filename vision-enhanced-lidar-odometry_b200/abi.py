@@ -76,6 +76,8 @@ class BatchInputs(C.Structure):
 
 import numpy as np
 
+TRI_OBS3_DTYPE = np.dtype([("frame", np.int32), ("x", np.float32), ("y", np.float32), ("z", np.float32)])
+TRI_OBS2_DTYPE = np.dtype([("frame", np.int32), ("cam", np.int32), ("x", np.float32), ("y", np.float32)])
 ICP_CORR_DTYPE = np.dtype([
     ("src_ring", np.int32), ("src_idx", np.int32), ("np_s_i", np.int32), ("np_i", np.int32),
     ("np_s_j", np.int32), ("np_j", np.int32), ("np_k", np.int32), ("kept", np.int32),
@@ -93,7 +95,7 @@ EXPORTS = [
     "velo_gpu_device_name", "velo_gpu_host_alloc", "velo_gpu_host_free", "velo_gpu_timer_begin", "velo_gpu_timer_end",
     "velo_gpu_profile_enable", "velo_gpu_profile_reset", "velo_gpu_profile_read", "velo_gpu_kernel_name",
     "velo_gpu_scan_upload", "velo_gpu_scan_upload_rings", "velo_gpu_projection_upload", "velo_gpu_scan_info", "velo_gpu_scan_download", "velo_gpu_project",
-    "velo_gpu_project_download", "velo_gpu_depth_assoc", "velo_gpu_icp_pass", "velo_gpu_visual_residuals", "velo_gpu_frame_to_frame", "velo_gpu_match_hamming",
+    "velo_gpu_project_download", "velo_gpu_depth_assoc", "velo_gpu_icp_pass", "velo_gpu_visual_residuals", "velo_gpu_frame_to_frame", "velo_gpu_match_hamming", "velo_gpu_triangulate",
     "velo_gpu_batch_upload", "velo_gpu_batch_run", "velo_gpu_batch_download", "velo_gpu_batch_frontend", "velo_gpu_launch_count",
     "velo_gpu_batch_counts",
 ]

@@ -59,6 +59,7 @@ def lib():
     L.velo_gpu_visual_residuals.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
     L.velo_gpu_frame_to_frame.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]
     L.velo_gpu_match_hamming.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, C.POINTER(C.c_int), _P, _P]
+    L.velo_gpu_triangulate.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]
     L.velo_gpu_batch_upload.argtypes = [_P, C.c_int, C.c_int, _P]
     L.velo_gpu_batch_run.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
     L.velo_gpu_batch_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
@@ -314,6 +315,19 @@ class Context:
         self._ck(self.L.velo_gpu_match_hamming(self.h, _ptr(query) if nq else None, nq, _ptr(train) if nt else None, nt, db, match_thresh,
                                                _ptr(pairs), C.byref(n), _ptr(bi), _ptr(bd)))
         return pairs[:n.value], bi[:nq], bd[:nq]
+
+    def triangulate(self, off3, obs3, off2, obs2, poses, init_xyz=None, has_init=None):
+        """triangulatePoint (velo.h:1027-1130) for len(off3)-1 landmarks; obs3/obs2 structured arrays (abi.TRI_OBS*_DTYPE)"""
+        off3 = np.ascontiguousarray(off3, np.int32); off2 = np.ascontiguousarray(off2, np.int32)
+        obs3 = np.ascontiguousarray(obs3, abi.TRI_OBS3_DTYPE); obs2 = np.ascontiguousarray(obs2, abi.TRI_OBS2_DTYPE)
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)
+        n = len(off3) - 1
+        out = np.zeros((max(n, 1), 3), np.float32); it = np.zeros(max(n, 1), np.int32)
+        ini = None if init_xyz is None else np.ascontiguousarray(init_xyz, np.float32)
+        has = None if has_init is None else np.ascontiguousarray(has_init, np.int32)
+        self._ck(self.L.velo_gpu_triangulate(self.h, n, _ptr(off3), _ptr(obs3) if len(obs3) else None, _ptr(off2), _ptr(obs2) if len(obs2) else None,
+                                             _ptr(poses) if len(poses) else None, len(poses), _ptr(ini), _ptr(has), _ptr(out), _ptr(it)))
+        return out[:n], it[:n]
 
     # ---- batched path
     def batch_upload(self, slot0, batch):

@@ -731,6 +731,44 @@ extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, 
     return VELO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ batched triangulation (f3)
+extern "C" int velo_gpu_triangulate(velo_gpu_ctx *ctx, int n, const int *off3, const velo_tri_obs3 *obs3, const int *off2, const velo_tri_obs2 *obs2,
+                                    const double *camera_poses, int n_frames, const float *init_xyz, const int *has_init, float *out_xyz, int *iterations) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (n < 0 || n_frames < 0 || (n > 0 && (!off3 || !off2 || !out_xyz)) || (has_init && !init_xyz)) return fail(ctx, VELO_ERR_INVALID_ARG, "bad triangulation arguments");
+    if (n == 0) return VELO_OK;
+    for (int l = 0; l < n; l++) if (off3[l + 1] < off3[l] || off2[l + 1] < off2[l]) return fail(ctx, VELO_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    const int n3 = off3[n] - off3[0], n2 = off2[n] - off2[0];
+    if (off3[0] != 0 || off2[0] != 0 || (n3 > 0 && !obs3) || (n2 > 0 && !obs2) || ((n3 + n2) > 0 && !camera_poses)) return fail(ctx, VELO_ERR_INVALID_ARG, "bad observation arrays");
+    CK(cudaSetDevice(ctx->device));
+    // scratch for this call (landmark batches are small next to the scans; no persistent buffers are kept)
+    int *d_off3 = nullptr, *d_off2 = nullptr, *d_has = nullptr, *d_it = nullptr; velo_tri_obs3 *d_o3 = nullptr; velo_tri_obs2 *d_o2 = nullptr;
+    double *d_poses = nullptr; float *d_init = nullptr, *d_out = nullptr;
+    int rc = VELO_OK;
+#define TRY(call) do { if (rc == VELO_OK && (call) != cudaSuccess) rc = fail(ctx, VELO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); } while (0)
+    TRY(cudaMalloc((void **)&d_off3, (n + 1) * sizeof(int))); TRY(cudaMalloc((void **)&d_off2, (n + 1) * sizeof(int)));
+    TRY(cudaMalloc((void **)&d_o3, (size_t)(n3 > 0 ? n3 : 1) * sizeof(velo_tri_obs3))); TRY(cudaMalloc((void **)&d_o2, (size_t)(n2 > 0 ? n2 : 1) * sizeof(velo_tri_obs2)));
+    TRY(cudaMalloc((void **)&d_poses, (size_t)(n_frames > 0 ? n_frames : 1) * 6 * sizeof(double)));
+    TRY(cudaMalloc((void **)&d_out, (size_t)n * 3 * sizeof(float))); TRY(cudaMalloc((void **)&d_it, n * sizeof(int)));
+    if (has_init) { TRY(cudaMalloc((void **)&d_has, n * sizeof(int))); TRY(cudaMalloc((void **)&d_init, (size_t)n * 3 * sizeof(float))); }
+    TRY(cudaMemcpyAsync(d_off3, off3, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(cudaMemcpyAsync(d_off2, off2, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (n3 > 0) TRY(cudaMemcpyAsync(d_o3, obs3, (size_t)n3 * sizeof(velo_tri_obs3), cudaMemcpyHostToDevice, ctx->stream));
+    if (n2 > 0) TRY(cudaMemcpyAsync(d_o2, obs2, (size_t)n2 * sizeof(velo_tri_obs2), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_frames > 0) TRY(cudaMemcpyAsync(d_poses, camera_poses, (size_t)n_frames * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (has_init) { TRY(cudaMemcpyAsync(d_has, has_init, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); TRY(cudaMemcpyAsync(d_init, init_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); }
+    if (rc == VELO_OK) {
+        launch_triangulate(launcher(ctx), n, d_off3, d_o3, d_off2, d_o2, d_poses, n_frames, ctx->dcal, ctx->prm.loss_thresh_3D2D, ctx->prm.weight_3D2D, d_init, d_has, d_out, d_it);
+        TRY(cudaGetLastError());
+        TRY(cudaMemcpyAsync(out_xyz, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (iterations) TRY(cudaMemcpyAsync(iterations, d_it, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(cudaStreamSynchronize(ctx->stream));
+    }
+#undef TRY
+    cudaFree(d_off3); cudaFree(d_off2); cudaFree(d_o3); cudaFree(d_o2); cudaFree(d_poses); cudaFree(d_out); cudaFree(d_it); cudaFree(d_has); cudaFree(d_init);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ Hamming matcher (f4)
 extern "C" int velo_gpu_match_hamming(velo_gpu_ctx *ctx, const uint8_t *query, int n_query, const uint8_t *train, int n_train, int desc_bytes,
                                       double match_thresh, int *pairs, int *n_pairs, int *best_idx, int *best_dist) {

@@ -146,3 +146,6 @@ void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr
                      double loss_a, double weight, double *partial, int ctas, double *out);
 void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const double *e_vis);
 void launch_hamming(const Launcher &L, const unsigned long long *q, int nq, const unsigned long long *t, int nt, int words, int *best_idx, int *best_dist);
+void launch_triangulate(const Launcher &L, int n, const int *off3, const velo_tri_obs3 *obs3, const int *off2, const velo_tri_obs2 *obs2,
+                        const double *poses, int n_frames, const DevCalib &cal, double loss_a, double weight,
+                        const float *init_xyz, const int *has_init, float *out_xyz, int *iterations);

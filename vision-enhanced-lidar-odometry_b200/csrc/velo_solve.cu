@@ -6,7 +6,7 @@
 // launches with no host round trip until its result is read.
 //
 // The trust-region policy restates Ceres' documented defaults [recall; Ceres is not in /root/reference, parity for this row is
-// "to solver tolerance" and defined by oracle/velo_oracle.cpp's identical restatement]: Levenberg-Marquardt,
+// "to solver tolerance" and defined by the CPU checker's identical restatement]: Levenberg-Marquardt,
 // initial_trust_region_radius 1e4, min/max_lm_diagonal 1e-6/1e32, min_relative_decrease 1e-3,
 // radius /= max(1/3, 1-(2 rho-1)^3) on success, radius /= 2,4,8.. on failure, function/gradient/parameter tolerances
 // 1e-6 / 1e-10 / 1e-8, max_num_iterations 50.

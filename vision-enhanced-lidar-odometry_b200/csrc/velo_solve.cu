@@ -17,7 +17,7 @@
 __global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo_icp_corr *__restrict__ corr, int cap, int src_slot,
                                                         const double *__restrict__ pose, const int *__restrict__ done,
                                                         double loss_a, double weight, double *__restrict__ partial) {
-    __shared__ double s_rows[8][32 * NEQ_ROW];
+    __shared__ double s_rows[8][NEQ_STAGE];
     __shared__ double s_red[8 * 56];
     __shared__ int s_cnt;
     if (done && *done) return;

@@ -21,7 +21,7 @@ __device__ __forceinline__ void take(Blk &o, int type, int nres, const DJ *r) {
 __global__ void __launch_bounds__(VIS_THREADS) k_visual(DevBuffers B, DevCalib cal, const VisUnit *__restrict__ units, VisTun tn,
                                                         const int *__restrict__ lm_valid, const float4 *__restrict__ lm_xyz,
                                                         double *__restrict__ partial, VisMatchOut *__restrict__ mout, VisFixed fx) {
-    __shared__ double s_rows[VIS_THREADS / 32][32 * NEQ_ROW];
+    __shared__ double s_rows[VIS_THREADS / 32][NEQ_STAGE];
     __shared__ double s_red[(VIS_THREADS / 32) * 56];
     __shared__ int s_cnt[2];
     const VisUnit U = units[blockIdx.y];

@@ -105,3 +105,18 @@ def test_kitti_wire_formats(velo, tmp_path):
         velo.api.kitti_load_scan(tmp_path / "missing.bin")
     T = np.eye(4); T[0, 3] = 1.5; T[2, 3] = -0.25; T[1, 1] = 0.999999123
     assert velo.api.kitti_format_pose(T) == "1 0 0 1.5 0 0.999999 0 0 0 0 1 -0.25 "
+
+
+def test_query_atan2_error_bound():
+    """The pruning windows of the correspondence search are padded by 1e-5 rad for atan2_q (csrc/velo_common.cuh); its error,
+    emulated in float32 with the kernel's operation order and the coefficients read from the source, must stay below 2.5e-6."""
+    import importlib.util, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("check_atan2", os.path.join(root, "tools", "check_atan2.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    src = open(os.path.join(root, "vision-enhanced-lidar-odometry_b200", "csrc", "velo_common.cuh")).read()
+    body = src[src.index("float atan2_q("):src.index("float r = p * a;")]
+    coef = [float(x) for x in re.findall(r"([-+]? ?\d\.\d{10,})f", body.replace("- 0", "-0").replace("+ 0", "+0"))]
+    assert len(coef) == 6
+    assert np.allclose(sorted(abs(c) for c in coef), sorted(abs(float(c)) for c in mod.c), rtol=0, atol=1e-7)
+    assert mod.max_error(300_000) < 2.5e-6

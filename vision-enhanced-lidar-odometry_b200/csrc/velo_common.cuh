@@ -55,13 +55,31 @@ __device__ __forceinline__ void idx_frame(const DevCalib &cal, float x, float y,
     vy = cal.vtc[1] * dx + cal.vtc[5] * dy + cal.vtc[9] * dz;
     vz = cal.vtc[2] * dx + cal.vtc[6] * dy + cal.vtc[10] * dz;
 }
+// atan2 for the *pruning* geometry of a query (azimuth / elevation in the index frame): odd minimax polynomial of degree 11 on
+// [0,1] + octant fix-up, |error| < 2e-6 rad over all quadrants (checked against f64 atan2 on 2.4e7 points, tools/check_atan2.py);
+// asin_ub() pads every window by 1e-5 rad for it.  About a third of the instructions of atan2f.  Index *construction* keeps atan2f.
+__device__ __forceinline__ float atan2_q(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    const float a = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float s = a * a;
+    float p = -0.011719132173485577f;
+    p = p * s + 0.05264734316289409f; p = p * s - 0.11642647568056484f; p = p * s + 0.1935403746008874f;
+    p = p * s - 0.3326228279880411f; p = p * s + 0.9999772191230201f;
+    float r = p * a;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
 __device__ __forceinline__ int el_bucket(float el) {   // monotone non-decreasing in el (required for conservative masks)
     int b = (int)floorf((el - VELO_EL_MIN) * (VELO_EL_BUCKETS / (VELO_EL_MAX - VELO_EL_MIN)));
     return min(max(b, 0), VELO_EL_BUCKETS - 1);
 }
-__device__ __forceinline__ int rg_bucket(float rho) {   // monotone non-decreasing in rho
-    int b = (int)floorf(log2f(fmaxf(rho, VELO_RG_MIN) * (1.0f / VELO_RG_MIN)) * VELO_RG_PER_OCTAVE);
-    return min(max(b, 0), VELO_RG_BUCKETS - 1);
+// monotone non-decreasing in rho (all the masks need).  A float's exponent and top mantissa bits are a piecewise-linear log2:
+// VELO_RG_MANT_BITS mantissa bits = 64 buckets per octave from VELO_RG_MIN, four integer instructions instead of log2f.
+__device__ __forceinline__ int rg_bucket(float rho) {
+    const int b = (__float_as_int(fmaxf(rho, VELO_RG_MIN)) - __float_as_int(VELO_RG_MIN)) >> (23 - VELO_RG_MANT_BITS);
+    return min(b, VELO_RG_BUCKETS - 1);
 }
 __device__ __forceinline__ int az_bin(float az) {
     int b = (int)((az + CUDART_PI_F) * (VELO_AZ_BINS / (2.0f * CUDART_PI_F)));

@@ -49,7 +49,7 @@ struct Window { int b0, b1; bool wrapped, full; float gam, half; };
 // only used to size pruning windows, where "too large" is always safe)
 __device__ __forceinline__ float asin_ub(float x) {
     if (!(x < 0.999f)) return 4.0f;
-    return x * rsqrtf(1.0f - x * x) * (1.0f + 4e-6f) + 2e-5f;
+    return x * rsqrtf(1.0f - x * x) * (1.0f + 4e-6f) + 3e-5f;     // 2e-5 float slack + 1e-5 for atan2_q
 }
 // bins covered by [az - half, az + half]
 __device__ __forceinline__ void set_bins(Window &w, float az, float half) {
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
     __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
     __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];
-    __shared__ unsigned long long s_stat[VELO_MAX_PASSES][5];
+    __shared__ unsigned long long s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];   // per warp: no atomics
     __shared__ IcpPass s_pass[VELO_MAX_PASSES];
     const IcpUnit &U = units[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     for (int i = tid; i < (int)(NP * sizeof(IcpPass) / sizeof(double)); i += blockDim.x)
         reinterpret_cast<double *>(s_pass)[i] = reinterpret_cast<const double *>(U.pass)[i];
     for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 56; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
-    for (int i = tid; i < VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0])[i] = 0ull;
+    for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0][0])[i] = 0ull;
     if (tid == 0) {
         int q = 0;
         for (int s = 0; s < nrM; s++) { s_q[s] = q; int r0 = rsM[s], L = rsM[s + 1] - r0; s_rsM[s] = r0; q += (L + skip - 1) / skip; }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             // ---- pruning geometry of the query in the index frame of the target scan
             float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
             const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
-            const float az = atan2f(vy, vx), el = atan2f(vz, D);
+            const float az = atan2_q(vy, vx), el = atan2_q(vz, D);
             const int bq = az_bin(az);
 
             u64 ki = KEY_INF, kj = KEY_INF;
@@ -412,15 +412,14 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 } else if (fr == 6 && c0 == 6) { rec[27] += ch; rec[55] += 0.5 * cr0; }
             }
 #endif
-            int c_kept = kept ? 1 : 0;
-            for (int o = 16; o > 0; o >>= 1) {
-                c_kept += __shfl_down_sync(FULL, c_kept, o);
-                st_seed += __shfl_down_sync(FULL, st_seed, o); st_exh += __shfl_down_sync(FULL, st_exh, o);
-                st_rings += __shfl_down_sync(FULL, st_rings, o); st_mask += __shfl_down_sync(FULL, st_mask, o);
-            }
-            if (lane == 0) {
-                atomicAdd(&s_stat[ps][0], (u64)c_kept); atomicAdd(&s_stat[ps][1], (u64)st_seed); atomicAdd(&s_stat[ps][2], (u64)st_exh);
-                atomicAdd(&s_stat[ps][3], (u64)st_rings); atomicAdd(&s_stat[ps][4], (u64)st_mask);
+            {   // search statistics of the pass: one REDUX per counter, lane 0 adds them to the warp's own counters
+                const unsigned r_kept = __popc(__ballot_sync(FULL, kept));
+                const unsigned r_seed = __reduce_add_sync(FULL, (unsigned)st_seed), r_exh = __reduce_add_sync(FULL, (unsigned)st_exh);
+                const unsigned r_rings = __reduce_add_sync(FULL, (unsigned)st_rings), r_mask = __reduce_add_sync(FULL, (unsigned)st_mask);
+                if (lane == 0) {
+                    unsigned long long *st = s_stat[wid][ps];
+                    st[0] += r_kept; st[1] += r_seed; st[2] += r_exh; st[3] += r_rings; st[4] += r_mask;
+                }
             }
         }
     }
@@ -434,8 +433,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     }
     if (tid < NP) {
         double *po = pbase + tid * 64;
-        po[56] = (double)s_stat[tid][0]; po[57] = (double)s_stat[tid][0]; po[58] = (double)(q1 > q0 ? q1 - q0 : 0);
-        po[59] = (double)s_stat[tid][1]; po[60] = (double)s_stat[tid][2]; po[61] = (double)s_stat[tid][3]; po[62] = (double)s_stat[tid][4]; po[63] = 0.0;
+        unsigned long long st[5] = { 0ull, 0ull, 0ull, 0ull, 0ull };
+        for (int wq = 0; wq < ICP_THREADS / 32; wq++) for (int k = 0; k < 5; k++) st[k] += s_stat[wq][tid][k];
+        po[56] = (double)st[0]; po[57] = (double)st[0]; po[58] = (double)(q1 > q0 ? q1 - q0 : 0);
+        po[59] = (double)st[1]; po[60] = (double)st[2]; po[61] = (double)st[3]; po[62] = (double)st[4]; po[63] = 0.0;
     }
 }
 

@@ -125,6 +125,7 @@ def run_ours(args, rank, world, local_rank):
     cal = api.calib_from_kitti(P, Tr, w, h)
     prm = api.default_params(max_slots=T + 1, max_points=131072, max_rings=64, max_features=args.features, max_matches=args.features,
                              icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
+    if args.icp_ctas > 0: prm.ctas_per_icp_unit = args.icp_ctas
     ctx = api.Context(prm, cal, device=local_rank)
     pool = api.PinnedPool()
     frame0 = 1000 + rank * T          # frame-sharded: rank g owns frames [frame0, frame0 + T) plus the halo frame0 - 1
@@ -306,6 +307,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frame pairs per GPU per step")
     ap.add_argument("--features", type=int, default=2000)
     ap.add_argument("--icp-skip", type=int, default=1)
+    ap.add_argument("--icp-ctas", type=int, default=0, help="CTAs per frame pair of the correspondence kernel (0 = library default)")
     ap.add_argument("--rig", type=int, default=0, help="0 = KITTI stereo, 1 = off-road 4-camera rig")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -293,7 +293,7 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(cudaMallocHost((void **)&ctx->h_icp_units, n_icp_units * sizeof(IcpUnit)));
     CKC(cudaMallocHost((void **)&ctx->h_vis_units, n_vis_units * sizeof(VisUnit)));
     CKC(dalloc(ctx, &ctx->d_icp_units, n_icp_units)); CKC(dalloc(ctx, &ctx->d_vis_units, n_vis_units));
-    size_t part = n_icp_units * 32; if (part < (size_t)ctx->icp_partial_ctas) part = ctx->icp_partial_ctas;
+    const size_t part = n_icp_units * (size_t)launch_icp_runs_cap((int)N);     // one record per run of queries (velo_icp.cu)
     CKC(dalloc(ctx, &ctx->d_icp_partial, part * VELO_MAX_PASSES * 64)); CKC(dalloc(ctx, &ctx->d_icp_out, S * P * VELO_NEQ_STRIDE));
     ctx->vis_ctas = 0;
     size_t vpart = n_vis_units * 4; if (vpart < 64) vpart = 64;

@@ -135,8 +135,9 @@ void launch_ingest(const Launcher &L, const DevBuffers &B, const DevCalib &cal, 
 void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
 void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams);
-// units: device array [n_units]; partial: [n_units][ctas][VELO_MAX_PASSES][64] doubles; out: [n_units][out_stride_passes][VELO_NEQ_STRIDE];
+// units: device array [n_units]; partial: [n_units][launch_icp_runs_cap(B.N)][VELO_MAX_PASSES][64] doubles; out: [n_units][out_stride_passes][VELO_NEQ_STRIDE];
 // corr optional (single unit, records of its last pass)
+int launch_icp_runs_cap(int max_points);
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
                 double *partial, double *out, int out_stride_passes, velo_icp_corr *corr);
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,

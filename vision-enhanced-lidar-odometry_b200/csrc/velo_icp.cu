@@ -128,22 +128,34 @@ __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 
 // grid = (ctas per unit, n_units).  A unit is one frame pair with up to VELO_MAX_PASSES supplied poses (the ICP passes of
 // frameToFrame, velo.h:616,800).  One thread = one query point at a time, looping over the passes: the correspondence of
 // pass p (two real target points) seeds pass p+1 with an immediately tight bound, so only the first pass needs the probe.
+// Work distribution: the unit's queries are cut into BLOCKS of ICP_WARPS x ICP_RUN_CHUNKS chunks of 32 consecutive queries; RUN w
+// of a block is its chunks w, w + ICP_WARPS, w + 2 ICP_WARPS, ... (so the warps of a CTA that work on the runs of one block
+// sweep neighbouring queries at the same time and share L1 lines).  A CTA owns a contiguous range of blocks and its warps take
+// runs from a shared counter (search cost per query varies 10x; static striding left 13 % of the warp time waiting at the CTA's
+// end).  Each run's sums go to its own record of `partial`, indexed by the run's number in the unit, and k_neq_reduce adds the
+// records in run order: the result does not depend on which warp took which run.
+#ifndef ICP_RUN_CHUNKS
+#define ICP_RUN_CHUNKS 4
+#endif
+#define ICP_WARPS (ICP_THREADS / 32)
+#define ICP_BLOCK_QUERIES (32 * ICP_RUN_CHUNKS * ICP_WARPS)
+__host__ __device__ inline int icp_blocks(int queries) { return (queries + ICP_BLOCK_QUERIES - 1) / ICP_BLOCK_QUERIES; }
+__host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(max_points) * ICP_WARPS; }
+
 __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
-                                                          double *__restrict__ partial, velo_icp_corr *__restrict__ corr) {
+                                                          double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
     __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
-    __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];
+    __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
     __shared__ unsigned long long s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];   // per warp: no atomics
     __shared__ IcpPass s_pass[VELO_MAX_PASSES];
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = 0;
     const IcpUnit &U = units[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NP = U.n_pass;
-    double *pbase = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * VELO_MAX_PASSES * 64;
-    if (U.src_slot < 0) {   // unit without a previous scan: contributes nothing
-        for (int i = tid; i < VELO_MAX_PASSES * 64; i += blockDim.x) pbase[i] = 0.0;
-        return;
-    }
+    if (U.src_slot < 0) return;   // unit without a previous scan: contributes nothing (k_neq_reduce writes its zeros)
     const int nrM = B.n_rings[U.src_slot];
     const int *rsM = B.ring_start + (size_t)U.src_slot * (B.R + 1);
     const int *rsS = B.ring_start + (size_t)U.tgt_slot * (B.R + 1);
@@ -159,8 +171,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     }
     __syncthreads();
     const int Q = s_q[nrM];
-    const int per = (((Q + gridDim.x - 1) / gridDim.x) + 31) & ~31;
-    const int q0 = blockIdx.x * per, q1 = min(Q, q0 + per);
+    const int nblk = icp_blocks(Q), blk_per = (nblk + gridDim.x - 1) / gridDim.x;
+    const int blk0 = blockIdx.x * blk_per, blk1 = min(nblk, blk0 + blk_per);
+    const int q1 = Q;
+    double *pbase = partial + (size_t)blockIdx.y * runs_cap * VELO_MAX_PASSES * 64;
     const float4 *ptsM = B.pts + (size_t)U.src_slot * B.N;
     const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
@@ -171,8 +185,18 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const u64 *rloS = B.rmask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
     const u64 *rhiS = B.rmask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
 
-    for (int qb = q0; qb < q1; qb += ICP_THREADS) {
-        const int q = qb + tid;
+    for (;;) {
+        int run = 0;
+        if (lane == 0) run = atomicAdd(&s_next, 1);
+        run = __shfl_sync(FULL, run, 0);
+        const int blk = blk0 + run / ICP_WARPS, rw = run % ICP_WARPS;
+        if (blk >= blk1) break;
+        int nq = 0;
+      for (int ci = 0; ci < ICP_RUN_CHUNKS; ci++) {
+        const int qb = blk * ICP_BLOCK_QUERIES + (rw + ci * ICP_WARPS) * 32;
+        if (qb >= q1) break;
+        nq += min(q1 - qb, 32);
+        const int q = qb + lane;
         const bool active = q < q1;
         int sm = 0, smi = 0;
         float4 pm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -422,42 +446,68 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 }
             }
         }
-    }
-    __syncthreads();
-    // per-CTA partials, fixed warp order
-    for (int i = tid; i < NP * 56; i += blockDim.x) {
-        const int ps = i / 56, t = i % 56;
-        double s = 0.0;
-        for (int wq = 0; wq < ICP_THREADS / 32; wq++) s += s_acc[wq][ps][t];
-        pbase[ps * 64 + t] = s;
-    }
-    if (tid < NP) {
-        double *po = pbase + tid * 64;
-        unsigned long long st[5] = { 0ull, 0ull, 0ull, 0ull, 0ull };
-        for (int wq = 0; wq < ICP_THREADS / 32; wq++) for (int k = 0; k < 5; k++) st[k] += s_stat[wq][tid][k];
-        po[56] = (double)st[0]; po[57] = (double)st[0]; po[58] = (double)(q1 > q0 ? q1 - q0 : 0);
-        po[59] = (double)st[1]; po[60] = (double)st[2]; po[61] = (double)st[3]; po[62] = (double)st[4]; po[63] = 0.0;
+      }
+        // flush the run: record [run number in the unit][pass] = {56 sums, kept, kept, queries, 4 search counters}; then clear
+        __syncwarp();
+        {
+            double *po = pbase + (size_t)(blk * ICP_WARPS + rw) * VELO_MAX_PASSES * 64;
+            for (int i = lane; i < NP * 64; i += 32) {
+                const int ps = i >> 6, t = i & 63;
+                double v = 0.0;
+                if (t < 56) { v = s_acc[wid][ps][t]; s_acc[wid][ps][t] = 0.0; }
+                else if (t == 58) v = (double)nq;
+                else if (t < 63) { const int k = (t <= 57) ? 0 : t - 58; v = (double)s_stat[wid][ps][k]; }
+                po[i] = v;
+            }
+            __syncwarp();
+            for (int i = lane; i < NP * 5; i += 32) (&s_stat[wid][0][0])[i] = 0ull;
+            __syncwarp();
+        }
     }
 }
 
-// fixed-order sum of the per-CTA partials of one (unit, pass): out[unit][pass][0..62]
-__global__ void k_neq_reduce(const double *__restrict__ partial, double *__restrict__ out, int ctas, int out_stride_passes) {
-    const int u = blockIdx.x, ps = blockIdx.y, t = threadIdx.x;
-    if (t >= VELO_NEQ_STRIDE) return;
-    double s = 0.0;
-    if (t < 63) for (int c = 0; c < ctas; c++) s += partial[(((size_t)u * ctas + c) * VELO_MAX_PASSES + ps) * 64 + t];
-    out[((size_t)u * out_stride_passes + ps) * VELO_NEQ_STRIDE + t] = s;
+// fixed-order sum of the per-run records of one (unit, pass): out[unit][pass][0..62]
+__global__ void __launch_bounds__(256) k_neq_reduce(DevBuffers B, const IcpUnit *__restrict__ units, const double *__restrict__ partial, int runs_cap,
+                                                    double *__restrict__ out, int out_stride_passes) {
+    __shared__ double s_part[4][64];
+    __shared__ int s_runs;
+    const int u = blockIdx.x, ps = blockIdx.y, t = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const IcpUnit &U = units[u];
+    if (threadIdx.x == 0) {
+        int q = 0;
+        if (U.src_slot >= 0 && ps < U.n_pass) {
+            const int *rs = B.ring_start + (size_t)U.src_slot * (B.R + 1);
+            const int nr = B.n_rings[U.src_slot];
+            for (int s = 0; s < nr; s++) q += (rs[s + 1] - rs[s] + U.skip - 1) / U.skip;
+        }
+        s_runs = icp_blocks(q) * ICP_WARPS;
+    }
+    __syncthreads();
+    const int runs = s_runs;
+    const double *p = partial + ((size_t)u * runs_cap * VELO_MAX_PASSES + ps) * 64 + t;
+    double s = 0.0;                                      // four interleaved partial sums (run % 4), combined in a fixed order
+    for (int r = g; r < runs; r += 4) s += p[(size_t)r * VELO_MAX_PASSES * 64];
+    s_part[g][t] = s;
+    __syncthreads();
+    if (threadIdx.x < VELO_NEQ_STRIDE) {
+        double v = 0.0;
+        if (t < 63) v = ((s_part[0][t] + s_part[1][t]) + s_part[2][t]) + s_part[3][t];
+        out[((size_t)u * out_stride_passes + ps) * VELO_NEQ_STRIDE + threadIdx.x] = v;
+    }
 }
+
+int launch_icp_runs_cap(int max_points) { return icp_runs_cap(max_points); }
 
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
                 double *partial, double *out, int out_stride_passes, velo_icp_corr *corr) {
     if (n_units <= 0) return;
+    const int runs_cap = icp_runs_cap(B.N);
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
-    k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, corr);
+    k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr);
     if (L.post) L.post(L.user, VK_ICP_PASS);
     dim3 g2(n_units, n_pass);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);
-    k_neq_reduce<<<g2, 64, 0, L.stream>>>(partial, out, ctas, out_stride_passes);
+    k_neq_reduce<<<g2, 256, 0, L.stream>>>(B, units, partial, runs_cap, out, out_stride_passes);
     if (L.post) L.post(L.user, VK_NEQ_REDUCE);
 }

@@ -120,3 +120,17 @@ def test_query_atan2_error_bound():
     assert len(coef) == 6
     assert np.allclose(sorted(abs(c) for c in coef), sorted(abs(float(c)) for c in mod.c), rtol=0, atol=1e-7)
     assert mod.max_error(300_000) < 2.5e-6
+
+
+def test_no_fused_packed_f32_in_product_sass():
+    """Hazard H14: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit rounding and -fmad=false
+    (the scalar forms are respected).  The candidate distance uses FADD2 / FMUL2 only for operations that do not feed a packed
+    add; a fused packed op anywhere in the product library would silently break bit-exact indices."""
+    import shutil, subprocess
+    so = os.path.join(ROOT, "vision-enhanced-lidar-odometry_b200", "libvelo_gpu.so")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(so) or not os.path.exists(cuobjdump):
+        pytest.skip("library or cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
+    assert "FMUL2" in sass and "FADD2" in sass          # the packed path is really there
+    assert "FFMA2" not in sass

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -15,7 +16,8 @@ struct ProfRec { int k; cudaEvent_t a, b; };
 
 struct velo_gpu_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;   // stream2: every other chunk of batch_frontend
+    cudaStream_t launch_stream = nullptr;                                        // stream of the launch being profiled
     std::vector<cudaEvent_t> chunk_ev;
     velo_gpu_params prm;
     velo_gpu_calib cal;
@@ -230,15 +232,16 @@ static cudaEvent_t get_event(velo_gpu_ctx *c) {
 static void prof_pre(void *u, int k) {
     velo_gpu_ctx *c = (velo_gpu_ctx *)u; c->launches++;
     if (!c->profile) return;
-    c->cur_a = get_event(c); cudaEventRecord(c->cur_a, c->stream);
+    c->cur_a = get_event(c); cudaEventRecord(c->cur_a, c->launch_stream);
 }
 static void prof_post(void *u, int k) {
     velo_gpu_ctx *c = (velo_gpu_ctx *)u;
     if (!c->profile) return;
-    cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream);
+    cudaEvent_t b = get_event(c); cudaEventRecord(b, c->launch_stream);
     c->recs.push_back(ProfRec{ k, c->cur_a, b });
 }
-static Launcher launcher(velo_gpu_ctx *c) { return Launcher{ c->stream, prof_pre, prof_post, c }; }
+static Launcher launcher_on(velo_gpu_ctx *c, cudaStream_t st) { c->launch_stream = st; return Launcher{ st, prof_pre, prof_post, c }; }
+static Launcher launcher(velo_gpu_ctx *c) { return launcher_on(c, c->stream); }
 
 // ------------------------------------------------------------------------------------------------ lifecycle
 template <class T> static cudaError_t dalloc(velo_gpu_ctx *c, T **p, size_t n) {
@@ -333,6 +336,7 @@ extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VELO_OK;
@@ -887,12 +891,11 @@ extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, co
     return upload_range(ctx, slot0, 0, count, in, ctx->stream);
 }
 
-extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int first_has_prev) {
-    if (!ctx) return VELO_ERR_INVALID_ARG;
-    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
+// the selected stages for slots [slot0, slot0 + count) on L.stream; partial-sum areas are addressed by slot, so launches for
+// disjoint slot ranges may run concurrently on different streams
+static int run_stages(velo_gpu_ctx *ctx, const Launcher &L, int slot0, int count, int stages, int first_has_prev) {
     const DevBuffers &B = ctx->B;
-    Launcher L = launcher(ctx);
+    cudaStream_t st = L.stream;
     if (stages & VELO_STAGE_INGEST) launch_ingest(L, B, ctx->dcal, slot0, count);
     if (stages & VELO_STAGE_INDEX) launch_index(L, B, ctx->dcal, slot0, count);
     if (stages & VELO_STAGE_PROJECT) launch_project(L, B, ctx->dcal, slot0, count);
@@ -902,20 +905,28 @@ extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int s
     if ((stages & VELO_STAGE_ICP) && pairs > 0 && ctx->batch_passes > 0) {
         const int n_units = pairs;
         const int ctas = auto_ctas(ctx, n_units, 32);
-        if (skip_first) CK(cudaMemsetAsync(ctx->d_icp_out + (size_t)slot0 * B.P * VELO_NEQ_STRIDE, 0, (size_t)B.P * VELO_NEQ_STRIDE * sizeof(double), ctx->stream));
-        launch_icp(L, B, ctx->dcal, ctx->d_icp_units + s_first, n_units, ctx->batch_passes, ctas, ctx->d_icp_partial,
+        if (skip_first) CK(cudaMemsetAsync(ctx->d_icp_out + (size_t)slot0 * B.P * VELO_NEQ_STRIDE, 0, (size_t)B.P * VELO_NEQ_STRIDE * sizeof(double), st));
+        launch_icp(L, B, ctx->dcal, ctx->d_icp_units + s_first, n_units, ctx->batch_passes, ctas,
+                   ctx->d_icp_partial + (size_t)s_first * launch_icp_runs_cap(B.N) * VELO_MAX_PASSES * 64,
                    ctx->d_icp_out + (size_t)s_first * B.P * VELO_NEQ_STRIDE, B.P, nullptr);
     }
     if ((stages & VELO_STAGE_VISUAL) && pairs > 0 && ctx->batch_vis > 0) {
         const int V = ctx->prm.f2f_iterations;
         if (ctx->batch_vis != V) return fail(ctx, VELO_ERR_STATE, "batched visual stage needs n_vis_iters == f2f_iterations");
         const int n_units = pairs * V;
-        if (skip_first) CK(cudaMemsetAsync(ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, 0, (size_t)V * VELO_NEQ_STRIDE * sizeof(double), ctx->stream));
-        launch_visual(L, B, ctx->dcal, ctx->d_vis_units + (size_t)s_first * V, n_units, vis_tun(ctx), nullptr, nullptr, ctx->d_vis_partial,
-                      ctx->d_vis_out + (size_t)s_first * V * VELO_NEQ_STRIDE, nullptr, 4);
+        if (skip_first) CK(cudaMemsetAsync(ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, 0, (size_t)V * VELO_NEQ_STRIDE * sizeof(double), st));
+        launch_visual(L, B, ctx->dcal, ctx->d_vis_units + (size_t)s_first * V, n_units, vis_tun(ctx), nullptr, nullptr,
+                      ctx->d_vis_partial + (size_t)s_first * V * 4 * 64, ctx->d_vis_out + (size_t)s_first * V * VELO_NEQ_STRIDE, nullptr, 4);
     }
     CK(cudaGetLastError());
     return VELO_OK;
+}
+
+extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int first_has_prev) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return run_stages(ctx, launcher(ctx), slot0, count, stages, first_has_prev);
 }
 
 extern "C" int velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *icp_neq, double *vis_neq, int *has_depth, int *n_hits) {
@@ -940,25 +951,46 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
     if (!ctx || !in) return VELO_ERR_INVALID_ARG;
     if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (chunk <= 0) chunk = (count + 7) / 8;
+    // chunk boundaries: a fixed size if the caller gives one; otherwise a small first chunk (the only upload nothing can hide)
+    // doubling up to count/4, because every chunk ends with the tail of its own correspondence launch
+    std::vector<int> cut(1, 0);
+    if (chunk > 0) { for (int i = chunk; i < count; i += chunk) cut.push_back(i); }
+    else { const int cap = std::max(32, count / 4); for (int i = std::max(16, count / 64), n = i; i < count; n = std::min(2 * n, cap), i += n) cut.push_back(i); }
+    if (chunk <= 0 && cut.size() > 1 && count - cut.back() < 32) cut.pop_back();      // no tiny last chunk
+    cut.push_back(count);
+    const int nchunks = (int)cut.size() - 1;
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    const int nchunks = (count + chunk - 1) / chunk;
     while ((int)ctx->chunk_ev.size() < nchunks + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
     // the copy stream must not overwrite slots that earlier work on the compute stream may still read
     CK(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+    // chunks alternate between two compute streams, so the tail of one chunk's correspondence launch overlaps the next chunk's
+    // kernels; a chunk's frame pairs read the previous chunk's last scan, hence the wait on its index / projection stages
+    // (per-kernel profiling needs serial launches: one stream then)
+    if (!ctx->stream2) CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    const bool two = !ctx->profile && nchunks > 1;
+    while ((int)ctx->chunk_ev.size() < 2 * nchunks + 2) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    cudaEvent_t *ev_light = ctx->chunk_ev.data() + nchunks + 1;
+    if (two) CK(cudaStreamWaitEvent(ctx->stream2, ctx->chunk_ev[nchunks], 0));
+    const int light = VELO_STAGE_INGEST | VELO_STAGE_INDEX | VELO_STAGE_PROJECT | VELO_STAGE_ASSOC;
     for (int c = 0; c < nchunks; c++) {
-        const int i0 = c * chunk, n = (i0 + chunk <= count) ? chunk : count - i0;
-        int rc = upload_range(ctx, slot0, i0, n, in, ctx->copy_stream);
+        cudaStream_t st = (two && (c & 1)) ? ctx->stream2 : ctx->stream;
+        const Launcher L = launcher_on(ctx, st);
+        // host-side preparation of the chunk (pose packs: trigonometry + forward-mode dR per pass) and its copies are issued right
+        // before its kernels, so preparing chunk c+1 overlaps the device work of chunk c
+        int rc = upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
-    }
-    for (int c = 0; c < nchunks; c++) {
-        const int i0 = c * chunk, n = (i0 + chunk <= count) ? chunk : count - i0;
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
-        int rc = velo_gpu_batch_run(ctx, slot0 + i0, n, VELO_STAGE_ALL, 1);
+        CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+        rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], light, 1);
+        if (rc) return rc;
+        CK(cudaEventRecord(ev_light[c], st));
+        if (c > 0) CK(cudaStreamWaitEvent(st, ev_light[c - 1], 0));
+        rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], VELO_STAGE_ICP | VELO_STAGE_VISUAL, 1);
         if (rc) return rc;
     }
+    if (two) { CK(cudaEventRecord(ev_light[nchunks], ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ev_light[nchunks], 0)); }
+    ctx->launch_stream = ctx->stream;
     return velo_gpu_batch_download(ctx, slot0, count, icp_neq, vis_neq, has_depth, n_hits);
 }
 

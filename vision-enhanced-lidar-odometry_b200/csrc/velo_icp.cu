@@ -24,6 +24,11 @@
 #ifndef ICP_SCAN_CHUNK
 #define ICP_SCAN_CHUNK (1 << 30)   /* measured (tools/tune_chunk.sh): capping the candidates per round at 8/16/32 is 31/15/7 % slower */
 #endif
+#ifndef ICP_UNROLL
+#define ICP_UNROLL 4           /* candidate loads in flight per lane */
+#endif
+#define VELO_STR_(x) #x
+#define VELO_UNROLL(n) _Pragma(VELO_STR_(unroll n))
 #define KEY_INF 0xFFFFFFFFFFFFFFFFull
 
 __device__ __forceinline__ u64 make_key(float d2, int ring, int idx) {
@@ -77,7 +82,7 @@ __device__ __forceinline__ Window make_window(float d2b, float az, float D, floa
 __device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, int start, int end, float mx, float my, float mz, u64 &best, int &ncand) {
     ncand += max(end - start, 0);
     const u64 mxy = pack2f(mx, my);
-#pragma unroll 4
+    VELO_UNROLL(ICP_UNROLL)
     for (int p = start; p < end; p++) {
         const float4 c = __ldg(sorted + p);
         const float d2 = d2f_xy2(c, mxy, mz);

@@ -140,35 +140,52 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
 
 // Ring-mask tables: for (slot, sector, elevation bucket b)  mask_lo = { rings r : bucket(lo_r) <= b },  mask_hi = { r : bucket(hi_r) >= b }.
 // The rings whose elevation interval in that sector can intersect [e0, e1] are a subset of mask_lo[bucket(e1)] & mask_hi[bucket(e0)]
-// (bucket() is monotone), which turns the per-query 64-ring scan into two 8-byte loads per sector.
+// (bucket() is monotone), which turns the per-query 64-ring scan into two 8-byte loads per sector; the same over range buckets.
+// One CTA per (sector, slot), one thread per bucket: every ring sets its bit in the one bucket each of its four bounds falls in
+// (shared-memory atomicOr), then a prefix-OR (lo tables) / suffix-OR (hi tables) over the 256 buckets gives the cumulative masks.
+__device__ __forceinline__ unsigned long long block_or_scan_256(unsigned long long v, unsigned long long *s_w, int tid) {
+    // inclusive OR-scan over 256 threads (8 warps); s_w: 8 words
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, v, o); if (lane >= o) v |= t; }
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads();
+    unsigned long long pre = 0ull;
+    for (int k = 0; k < wid; k++) pre |= s_w[k];
+    __syncthreads();
+    return v | pre;
+}
 __global__ void __launch_bounds__(VELO_EL_BUCKETS) k_index_masks(DevBuffers B, int slot0) {
-    static_assert(VELO_EL_BUCKETS == VELO_RG_BUCKETS, "one thread per bucket of either table");
-    __shared__ short s_bk[VELO_MAX_RINGS_HARD][4];      // bucket(elev lo), bucket(elev hi), bucket(range min), bucket(range max); -1 = empty
+    static_assert(VELO_EL_BUCKETS == 256 && VELO_RG_BUCKETS == 256, "one thread per bucket of either table, 8 warps");
+    __shared__ unsigned long long s_set[4][VELO_EL_BUCKETS];   // bits of the rings whose bound falls into bucket b: elev lo, elev hi, range min, range max
+    __shared__ unsigned long long s_w[8];
     const int slot = slot0 + blockIdx.y, sec = blockIdx.x, b = threadIdx.x;
     const int nr = B.n_rings[slot];
     const float4 *se = B.sec_box + (size_t)slot * B.R * VELO_SECTORS + sec;
-    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
-        const float4 e = se[(size_t)r * VELO_SECTORS];
-        const bool ok = e.x <= e.y;                         // sector not empty for this ring
-        s_bk[r][0] = ok ? (short)el_bucket(e.x) : (short)-1; s_bk[r][1] = (short)el_bucket(e.y);
-        s_bk[r][2] = (short)rg_bucket(e.z); s_bk[r][3] = (short)rg_bucket(e.w);
-    }
-    __syncthreads();
     const size_t o = (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + b) * B.W;
     for (int w = 0; w < B.W; w++) {
-        unsigned long long lo = 0ull, hi = 0ull, rlo = 0ull, rhi = 0ull;
-        const int r1 = min(nr, (w + 1) * 64);
-        for (int r = w * 64; r < r1; r++) {
-            const int e0 = s_bk[r][0];
-            if (e0 >= 0) {
-                const unsigned long long bit = 1ull << (r & 63);
-                if (e0 <= b) lo |= bit;
-                if (s_bk[r][1] >= b) hi |= bit;
-                if (s_bk[r][2] <= b) rlo |= bit;
-                if (s_bk[r][3] >= b) rhi |= bit;
+#pragma unroll
+        for (int t = 0; t < 4; t++) s_set[t][b] = 0ull;
+        __syncthreads();
+        const int r = w * 64 + b;
+        if (b < 64 && r < nr) {
+            const float4 e = se[(size_t)r * VELO_SECTORS];
+            if (e.x <= e.y) {                                   // sector not empty for this ring
+                const unsigned long long bit = 1ull << b;
+                atomicOr(&s_set[0][el_bucket(e.x)], bit); atomicOr(&s_set[1][el_bucket(e.y)], bit);
+                atomicOr(&s_set[2][rg_bucket(e.z)], bit); atomicOr(&s_set[3][rg_bucket(e.w)], bit);
             }
         }
-        B.mask_lo[o + w] = lo; B.mask_hi[o + w] = hi; B.rmask_lo[o + w] = rlo; B.rmask_hi[o + w] = rhi;
+        __syncthreads();
+        const int rb = VELO_EL_BUCKETS - 1 - b;               // suffix-OR = prefix-OR over the reversed index
+        const unsigned long long lo = block_or_scan_256(s_set[0][b], s_w, b);
+        const unsigned long long hi = block_or_scan_256(s_set[1][rb], s_w, b);
+        const unsigned long long rlo = block_or_scan_256(s_set[2][b], s_w, b);
+        const unsigned long long rhi = block_or_scan_256(s_set[3][rb], s_w, b);
+        B.mask_lo[o + w] = lo; B.rmask_lo[o + w] = rlo;
+        const size_t orv = (((size_t)slot * VELO_SECTORS + sec) * VELO_EL_BUCKETS + rb) * B.W;
+        B.mask_hi[orv + w] = hi; B.rmask_hi[orv + w] = rhi;
+        __syncthreads();
     }
 }
 

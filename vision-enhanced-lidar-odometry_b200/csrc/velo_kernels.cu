@@ -352,11 +352,15 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
     __syncthreads();
     const bool fits = s_off[nr] <= ASSOC_CAP;
     if (fits) {
+        // 8-byte cp.async per projection: no register round trip, so the copies of all rings are in flight together
         for (int s = 0; s < nr; s++) {
             const float2 *src = proj + s_rs[s];
-            float2 *dst = s_proj + s_off[s];
-            for (int i = threadIdx.x; i < s_cnt[s]; i += blockDim.x) dst[i] = src[i];
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_proj + s_off[s]);
+            for (int i = threadIdx.x; i < s_cnt[s]; i += blockDim.x)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(src + i) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     const float2 *base = fits ? s_proj : proj;
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
             const bool act = k < F;
             const float2 kp = act ? B.kp[sc * B.F + k] : make_float2(0.f, 0.f);
             int last = -1, hit = 0;
-            float4 out = make_float4(0.f, 0.f, 0.f, 1.0f);
+            int h_s = 0, h_mid = 0, h_last = 0;          // the bracket of the hit; its interpolation (global gathers) runs after the rounds
             int s = nr, s_end = -1;
             if (act) {
                 if (kp.y >= ymin && kp.y < ymax) { const int bkt = min(max((int)((kp.y - ymin) * yscale), 0), ASSOC_YB - 1); s = s_first[bkt]; s_end = s_lastr[bkt]; }
@@ -416,29 +420,25 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
                     const float2 *ps = base + off[s];
                     int lo = 0, hi = cnt - 2, mid = 0;
                     bool found = false;
-                    while (lo <= hi) {                                           // velo.h:404-412
+                    float2 a = make_float2(0.f, 0.f), b = a;
+                    // velo.h:404-412 with the same sequence of mid points, written without early `continue`s: both neighbours are
+                    // read every step and lo / hi move by selects, so the 32 lanes of a round run one instruction stream
+                    while (lo <= hi && !found) {
                         mid = (lo + hi) >> 1;
-                        const float2 a = ps[mid];
-                        if (a.x > kp.x) { hi = mid - 1; continue; }
-                        const float2 b = ps[mid + 1];
-                        if (b.x <= kp.x) { lo = mid + 1; continue; }
-                        found = true;
+                        a = ps[mid]; b = ps[mid + 1];
+                        const bool left = a.x > kp.x, right = !left && (b.x <= kp.x);
+                        hi = left ? mid - 1 : hi; lo = right ? mid + 1 : lo;
+                        found = !left && !right;
+                    }
+                    if (found) {
                         if (last != -1) {
                             const float2 *pq = base + off[s - 1];
                             const float2 c = pq[last], d = pq[last + 1];
                             if (((a.y > kp.y) != (c.y > kp.y)) && width_ok(__fsub_rn(a.x, b.x), cal) && width_ok(__fsub_rn(c.x, d.x), cal)) {
-                                const float4 *vs = valid + s_rs[s], *vq = valid + s_rs[s - 1];
-                                float3 i1 = lerp3(vs[mid], vs[mid + 1], a.x, b.x, kp.x);          // velo.h:445-450
-                                float3 i2 = lerp3(vq[last], vq[last + 1], c.x, d.x, kp.x);        // velo.h:451-456
-                                float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                       // velo.h:457-462
-                                float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                       // velo.h:463-468
-                                float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
-                                out = make_float4(r.x, r.y, r.z, 1.0f);
-                                hit = 1;
+                                hit = 1; h_s = s; h_mid = mid; h_last = last;
                             }
                         }
                         last = mid;                                              // velo.h:483
-                        break;
                     }
                     if (!found) last = -1;                                       // velo.h:487-489
                     s = hit ? nr + 1 : s + 1;                                    // velo.h:490
@@ -447,7 +447,17 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
             }
             if (act) {
                 B.hit_tmp[sc * B.F + k] = hit;
-                if (hit) B.kpwd_tmp[sc * B.F + k] = out;
+                if (hit) {
+                    const float2 *ps = base + off[h_s], *pq = base + off[h_s - 1];
+                    const float2 a = ps[h_mid], b = ps[h_mid + 1], c = pq[h_last], d = pq[h_last + 1];
+                    const float4 *vs = valid + s_rs[h_s], *vq = valid + s_rs[h_s - 1];
+                    const float3 i1 = lerp3(vs[h_mid], vs[h_mid + 1], a.x, b.x, kp.x);       // velo.h:445-450
+                    const float3 i2 = lerp3(vq[h_last], vq[h_last + 1], c.x, d.x, kp.x);     // velo.h:451-456
+                    const float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                        // velo.h:457-462
+                    const float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                        // velo.h:463-468
+                    const float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
+                    B.kpwd_tmp[sc * B.F + k] = make_float4(r.x, r.y, r.z, 1.0f);
+                }
             }
         }
     }

@@ -313,6 +313,28 @@ def test_batched_path_equals_single_frame_path_and_oracle(velo, oracle, calib):
         c.close()
 
 
+def test_normal_equations_do_not_depend_on_the_launch_shape(velo, calib):
+    """sums are kept per run of 128 queries and added in run order, so the CTAs per frame pair (and hence which warp processed
+    which run) must not change a single bit of the result"""
+    outs = []
+    for ctas in (0, 1, 5, 32):
+        prm = velo.api.default_params(max_slots=3, max_features=200, max_matches=200, icp_skip=3)
+        prm.ctas_per_icp_unit = ctas
+        c = velo.api.Context(prm, calib)
+        try:
+            b = velo.synth.Batch(31, 3, prm)
+            c.batch_upload(0, b)
+            c.batch_run(0, 3)
+            icp = np.zeros((3, b.n_passes, velo.abi.NEQ_STRIDE))
+            c.batch_download(0, 3, icp, None, None, None)
+            outs.append(icp)
+        finally:
+            c.close()
+    assert outs[0][1:, :, 58].min() > 30000            # many runs per frame pair
+    for o in outs[1:]:
+        assert o.tobytes() == outs[0].tobytes()
+
+
 def test_round_trip_properties_at_full_size(velo, calib):
     """size-independent properties at BASELINE size (no oracle): ingest is a permutation of a rigid transform,
     projection survivors are a subsequence inside the FOV, has_depth is a stable enumeration, JtJ is PSD."""

@@ -2,7 +2,7 @@
 """bench.py — frames/s of the VELO per-frame front end (scan ingest + stereo depth association + ICP correspondence
 + J^T J) on synthetic KITTI-shaped data, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames T] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames T] [--impl ours|reference] [--pose-spread tight|spec]
 
 A step = one pass of the whole front end over a batch of T consecutive frames per GPU (T frame pairs + 1 halo scan):
 ingest/segment T+1 scans, build T+1 neighbour indices, project + associate (2 cameras x 2 keypoint sets) T frames,
@@ -10,7 +10,7 @@ f2f_iterations x icp_iterations = 6 ICP passes (icp_skip = 1, ~120k queries vs ~
 assemblies per frame pair, each reduced to 6x6 normal equations.  `value` times that with inputs resident in HBM;
 `e2e` times upload (pinned host -> device) + the same work + download of the results, through the C ABI.
 `--impl reference` times the CPU restatement of the reference path (oracle/, kd-tree per ring like PCL) on all host
-cores with the reference's own call pattern.  See DESIGN.md "Measurement".
+cores with the reference's own call pattern; it never loads the CUDA library.  See DESIGN.md "Measurement".
 """
 import argparse
 import importlib
@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "frames/s (scan+stereo assoc+ICP corr+J^TJ)"
+DTYPE = "f32 geometry/indices, f64 residuals+JtJ"
+MAX_POINTS = 131072
+RTOL_NEQ = 1e-4          # north_star: J^T J entries within 1e-4 relative
 
 
 def load_peak():
@@ -33,6 +36,22 @@ def load_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(args, world):
+    """The workload both arms are quoted on (identical dict in `--impl ours` and `--impl reference`; the reference arm times a
+    bounded sample of it, stated in its `cpu_baseline.sample`)."""
+    T, F, C = args.frames, args.features, (4 if args.rig == 1 else 2)
+    return {
+        "workload": f"{T}-frame synthetic KITTI sequence per GPU (BASELINE configs[1]+[2]"
+                    f"{', off-road rig configs[3]' if args.rig == 1 else ''}): ingest+index {T + 1} scans, project+associate {C} cams x 2 keypoint "
+                    f"sets x {F} features, 6 ICP passes/frame (icp_skip={args.icp_skip}, ~120k pts vs ~120k pts) + 2 visual assemblies/frame, "
+                    "6x6 normal equations",
+        "frames_per_step": T * world, "frames_per_gpu": T, "points_per_scan": 120000, "rings": 64, "cams": C,
+        "features_per_image": F, "icp_passes": 6, "icp_skip": args.icp_skip, "pose_spread": args.pose_spread,
+        "sharding": f"frames over {world} GPU(s), no collective on the data path",
+        "l2": f"inputs {(T + 1) * MAX_POINTS * 16 / 1e9:.2f} GB/step >> 126 MB L2 (no flush needed)",
+    }
 
 
 class ClockSampler:
@@ -80,10 +99,37 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def algorithmic_bytes(abi, prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_vis, kept):
+def bind_to_gpu_numa(index):
+    """Pin this process (and with it the pinned host buffers it allocates next: first touch) to the CPUs of the NUMA node the
+    GPU hangs off, read from sysfs through the GPU's PCI address.  Eight ranks that all stage from one socket share one
+    memory controller and one inter-socket link; bound ranks do not.  Best effort: returns what it did."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "node": node, "why": "no local CPUs in the allowed set"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "node": node, "cpus": len(cpus)}
+    except Exception as e:                        # noqa: BLE001 — a container without sysfs / NVML simply stays unbound
+        return {"bound": False, "why": type(e).__name__}
+
+
+def algorithmic_bytes(prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_vis):
     """Compulsory traffic per kernel class for one step (DESIGN.md 'Algorithmic bytes'): every input read once,
     every required output written once.  npnt/nr/ptot over the T+1 slots; frame pairs are slots 1..T."""
-    C, R = prm.num_cams, 0
+    C = prm.num_cams
     AZ, SEC = 1024, 64      # VELO_AZ_BINS, VELO_SECTORS of csrc/velo_dev.cuh
     n_all = float(npnt.sum()); rings_all = float(nr.sum())
     n_fr = float(npnt[1:].sum()); rings_fr = float(nr[1:].sum())
@@ -107,7 +153,29 @@ def algorithmic_bytes(abi, prm, npnt, nr, ptot, nhits, nkp, nmatch, n_passes, n_
     return b
 
 
+def oracle_parity(batch, prm, cal, icp, vis, frames=2):
+    """Frames 1..`frames` of the timed batch against the CPU oracle, outside the timed region: block / query counts equal, every
+    H / g / cost entry within the north-star tolerance.  Raises on a mismatch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import pyoracle
+    orc = pyoracle.Oracle()
+    sub = batch.view(0, frames + 1)
+    _, oicp, ovis = orc.bench_frames(sub, prm, cal, threads=min(frames, os.cpu_count() or 1) * 4, want_out=True)
+    worst = 0.0
+    for t in range(1, frames + 1):
+        for got, exp, is_icp in ((icp[t], oicp[t], True), (vis[t], ovis[t], False)):
+            for p in range(exp.shape[0]):
+                sc = np.abs(exp[p, :56]).max()
+                np.testing.assert_allclose(got[p, :56], exp[p, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
+                assert got[p, 56] == exp[p, 56] and (not is_icp or got[p, 58] == exp[p, 58]), (t, p, got[p, 56:59], exp[p, 56:59])
+                nz = np.abs(exp[p, :56]) > 1e-9 * sc
+                worst = max(worst, float(np.max(np.abs(got[p, :56][nz] - exp[p, :56][nz]) / np.abs(exp[p, :56][nz]))) if nz.any() else 0.0)
+    return {"frames": frames, "max_rel_err_neq": worst, "tolerance": RTOL_NEQ}
+
+
 def run_ours(args, rank, world, local_rank):
+    numa = bind_to_gpu_numa(local_rank) if not args.no_numa else {"bound": False, "why": "--no-numa"}
     velo = importlib.import_module("vision-enhanced-lidar-odometry_b200")
     api, synth, abi = velo.api, velo.synth, velo.abi
     shard = importlib.import_module("vision-enhanced-lidar-odometry_b200.shard")
@@ -123,20 +191,24 @@ def run_ours(args, rank, world, local_rank):
     T = args.frames
     P, Tr, w, h = synth.calib_raw(args.rig)
     cal = api.calib_from_kitti(P, Tr, w, h)
-    prm = api.default_params(max_slots=T + 1, max_points=131072, max_rings=64, max_features=args.features, max_matches=args.features,
+    prm = api.default_params(max_slots=T + 1, max_points=MAX_POINTS, max_rings=64, max_features=args.features, max_matches=args.features,
                              icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
     if args.icp_ctas > 0: prm.ctas_per_icp_unit = args.icp_ctas
     ctx = api.Context(prm, cal, device=local_rank)
     pool = api.PinnedPool()
     frame0 = 1000 + rank * T          # frame-sharded: rank g owns frames [frame0, frame0 + T) plus the halo frame0 - 1
     t_gen = time.time()
-    batch = synth.Batch(frame0 - 1, T + 1, prm, rig=args.rig, alloc=pool.zeros)
+    batch = synth.Batch(frame0 - 1, T + 1, prm, rig=args.rig, alloc=pool.zeros, pose_spread=args.pose_spread)
+    if args.scan_format == "xyz":
+        batch = batch.xyz(pool.zeros)
     t_gen = time.time() - t_gen
     icp = pool.zeros((T + 1, batch.n_passes, abi.NEQ_STRIDE), np.float64)
     vis = pool.zeros((T + 1, batch.n_vis, abi.NEQ_STRIDE), np.float64)
     hd = pool.zeros((T + 1, 2, prm.num_cams, prm.max_features), np.int32)
     nh = pool.zeros((T + 1, 2, prm.num_cams), np.int32)
-    h2d = sum(a.nbytes for a in (batch.scans, batch.n_points, batch.kp, batch.n_kp, batch.matches, batch.n_matches)) \
+    rec = batch.scans.shape[-1] * 4
+    scan_bytes = int(batch.n_points.max()) * rec * (T + 1)          # rows of the longest scan, not max_points (velo_api.cu upload_range)
+    h2d = scan_bytes + sum(a.nbytes for a in (batch.n_points, batch.kp, batch.n_kp, batch.matches, batch.n_matches)) \
         + (T + 1) * batch.n_passes * 400 + (T + 1) * batch.n_vis * 72
     d2h = icp.nbytes + vis.nbytes + hd.nbytes + nh.nbytes
 
@@ -153,7 +225,21 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x):
+        if dist is None:
+            return [x]
+        import torch
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    # ---------------- host -> device copy rate with every rank copying at once (what bounds `e2e` when many GPUs share one host)
     ctx.batch_upload(0, batch)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.batch_upload(0, batch); ctx.sync()
+    h2d_gbs = all_ranks(h2d / 1e9 / (time.perf_counter() - t0))
     ctx.profile(True)
     # ---------------- device-resident timing (`value`)
     for _ in range(args.warmup):
@@ -193,8 +279,7 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- roofline of the dominant kernel + per-kernel table
     npnt, nr, ptot, st = ctx.batch_counts(0, T + 1)
     assert (st == 0).all(), "a scan exceeded max_rings"
-    kept = icp[1:, :, 56].sum()
-    ab = algorithmic_bytes(abi, prm, npnt, nr, ptot, nh, batch.n_kp, batch.n_matches, batch.n_passes, batch.n_vis, kept)
+    ab = algorithmic_bytes(prm, npnt, nr, ptot, nh, batch.n_kp, batch.n_matches, batch.n_passes, batch.n_vis)
     peak, peak_src = load_peak()
     kernels = {}
     for name, (kms, n) in prof.items():
@@ -202,44 +287,70 @@ def run_ours(args, rank, world, local_rank):
         bytes_per_launch = ab.get(name, 0.0)
         kernels[name] = {"ms_per_launch": round(per_launch_ms, 4), "launches": n, "share": round(kms / ms, 4),
                          "alg_MB_per_launch": round(bytes_per_launch / 1e6, 2),
-                         "GBps": round(bytes_per_launch / 1e9 / (per_launch_ms * 1e-3), 1) if per_launch_ms > 0 else None}
+                         "GBps": round(bytes_per_launch / 1e9 / (per_launch_ms * 1e-3), 1) if per_launch_ms > 0 else None,
+                         "frac_of_peak": round(bytes_per_launch / 1e9 / (per_launch_ms * 1e-3) / peak, 4) if per_launch_ms > 0 else None}
     dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
-    traffic = None
+    traffic, instr = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-            if tj.get("kernel") == dom and tj.get("frames") == T:
+            if tj.get("kernel") == dom and tj.get("frames") == T and tj.get("pose_spread", "tight") == args.pose_spread:
                 traffic = tj.get("dram_bytes_per_launch")
+                if tj.get("warp_instructions"):
+                    instr = tj["warp_instructions"] / max(float(icp[1:, :, 58].sum()), 1.0)
     except Exception:
         pass
     ach = kernels[dom]["GBps"]
     roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
             "traffic": traffic, "peak_source": peak_src,
-            "note": "icp_pass is compute/latency bound (exhaustive exact neighbour search), see DESIGN.md"}
+            "note": "icp_pass is instruction-issue / latency bound (exhaustive exact neighbour search), see DESIGN.md"}
 
+    cfg = workload_config(args, world)
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 geometry/indices, f64 residuals+JtJ", "data": "synthetic",
-        "config": {"workload": f"{T}-frame synthetic KITTI sequence per GPU (BASELINE configs[1]+[2]): ingest+index {T + 1} scans, "
-                               f"project+associate {prm.num_cams} cams x 2 keypoint sets x {args.features} features, "
-                               f"{batch.n_passes} ICP passes/frame (icp_skip={prm.icp_skip}, ~{int(npnt.mean())} pts vs ~{int(npnt.mean())} pts) + "
-                               f"{batch.n_vis} visual assemblies/frame, 6x6 normal equations",
-                   "frames_per_gpu": T, "points_per_scan": int(npnt.mean()), "rings": int(nr.mean()), "cams": prm.num_cams,
-                   "features_per_image": args.features, "icp_passes": batch.n_passes, "icp_skip": prm.icp_skip,
-                   "in_fov_per_cam": int(ptot[1:].mean()), "sharding": f"frames over {world} GPU(s), no collective on the data path",
-                   "l2": f"inputs {batch.scans.nbytes / 1e9:.2f} GB/step >> 126 MB L2 (no flush needed)"},
+        "dtype": DTYPE, "data": "synthetic",
+        "config": cfg,
+        "measured_shape": {"points_per_scan": int(npnt.mean()), "rings": int(nr.mean()), "in_fov_per_cam": int(ptot[1:].mean()),
+                           "depth_hits_per_image": int(nh[1:].mean()), "scan_format": args.scan_format,
+                           "equivalent_total_frames": f"{world * T} frames per step ({T} per GPU); configs[4]'s fixed 8000-frame sweep is this "
+                                                      "weak-scaling run at --frames 1000 --gpus 8, or any N with --frames 8000/N (frames are independent)"},
         "clocks": clk,
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(e2e_ms, 3)},
+        "h2d_GBps_per_rank_all_ranks_copying": [round(v, 1) for v in h2d_gbs],
+        "numa": numa,
         "gpu_launches": int(launches),
         "roofline": roof,
         "kernels": kernels,
         "gen_seconds": round(t_gen, 2),
         "icp_search": {"per_pass_candidates_per_query": [round(float((icp[1:, p, 59].sum() + icp[1:, p, 60].sum()) / max(icp[1:, p, 58].sum(), 1)), 1) for p in range(batch.n_passes)],
                        "per_pass_rings_scanned_per_query": [round(float(icp[1:, p, 61].sum() / max(icp[1:, p, 58].sum(), 1)), 2) for p in range(batch.n_passes)],
-                       "per_pass_kept_frac": [round(float(icp[1:, p, 56].sum() / max(icp[1:, p, 58].sum(), 1)), 3) for p in range(batch.n_passes)]},
+                       "per_pass_kept_frac": [round(float(icp[1:, p, 56].sum() / max(icp[1:, p, 58].sum(), 1)), 3) for p in range(batch.n_passes)],
+                       "warp_instr_per_query_pass": None if instr is None else round(instr, 1)},
     }
+    # ---------------- frame sharding gives the same bytes on every GPU: each rank recomputes rank 0's first frames
+    if dist is not None:
+        K = min(4, T)
+        same = synth.Batch(1000 - 1, K + 1, prm, rig=args.rig, pose_spread=args.pose_spread)
+        if args.scan_format == "xyz":
+            same = same.xyz()
+        icp_k = np.zeros((K + 1, batch.n_passes, abi.NEQ_STRIDE)); vis_k = np.zeros((K + 1, batch.n_vis, abi.NEQ_STRIDE))
+        hd_k = np.zeros((K + 1, 2, prm.num_cams, prm.max_features), np.int32); nh_k = np.zeros((K + 1, 2, prm.num_cams), np.int32)
+        if rank == 0:
+            mine = (icp[:K + 1].copy(), vis[:K + 1].copy(), hd[:K + 1].copy(), nh[:K + 1].copy())     # from the timed batch
+        ctx.batch_frontend(0, same, 0, icp_k, vis_k, hd_k, nh_k)
+        blob = np.concatenate([icp_k[1:, :, :59].ravel().view(np.uint8), vis_k[1:].ravel().view(np.uint8), hd_k[1:].ravel().view(np.uint8), nh_k[1:].ravel().view(np.uint8)])
+        allb = shard.gather_rows(dist, blob[None, :], dst=0, group=host_group)
+        if rank == 0:
+            ref_blob = np.concatenate([mine[0][1:, :, :59].ravel().view(np.uint8), mine[1][1:].ravel().view(np.uint8), mine[2][1:].ravel().view(np.uint8), mine[3][1:].ravel().view(np.uint8)])
+            out["shard_identical"] = bool(all(np.array_equal(allb[r], ref_blob) for r in range(world)))
+            out["shard_identical_what"] = f"frames 1000..{1000 + K - 1} recomputed by each of the {world} ranks on its own GPU: normal equations, has_depth, hit counts byte-identical to rank 0's timed batch"
+            assert out["shard_identical"], "per-frame outputs differ between GPUs"
+    if rank == 0 and not args.no_parity:
+        out["parity_checked"] = True
+        out["parity"] = oracle_parity(batch if args.scan_format == "kitti" else synth.Batch(frame0 - 1, 3, prm, rig=args.rig, pose_spread=args.pose_spread),
+                                      prm, cal, icp, vis, frames=2)
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, prm, cal, synth)
     ctx.close()
@@ -261,7 +372,7 @@ def cpu_baseline(args, prm, cal, synth, frames=None, threads=None):
     threads = threads or (os.cpu_count() or 1)
     frames = frames or threads      # one frame pair per host thread: measured to be the CPU's best configuration (0.70 vs 0.58 frames/s
                                     # with 4 threads splitting each frame on the 16-thread GPU box)
-    b = synth.Batch(999, frames + 1, prm, rig=args.rig)
+    b = synth.Batch(999, frames + 1, prm, rig=args.rig, pose_spread=args.pose_spread)
     sec, _, _ = orc.bench_frames(b, prm, cal, threads)
     return {"value": round(frames / sec, 4), "unit": "frames/s", "cores": threads, "kind": "port",
             "sample": f"{frames} frame pairs on {threads} host threads, same per-frame schedule as the GPU step, {sec:.1f} s wall",
@@ -270,15 +381,17 @@ def cpu_baseline(args, prm, cal, synth, frames=None, threads=None):
 
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU algorithm (oracle port: the reference itself cannot be built) on all
-    host threads; a step = `cores` frame pairs of the same workload."""
+    host threads; a step = `cores` frame pairs of the same workload.  Nothing of the CUDA product is loaded here: calibration and
+    tunables come from the oracle (oracle_calib_from_kitti, pyoracle.default_params), inputs from the host-side generator."""
     if rank != 0:
         return
-    velo = importlib.import_module("vision-enhanced-lidar-odometry_b200")
-    api, synth = velo.api, velo.synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    synth = importlib.import_module("vision-enhanced-lidar-odometry_b200.synth")      # host/velo_synth.c (gcc), no CUDA
     P, Tr, w, h = synth.calib_raw(args.rig)
-    cal = api.calib_from_kitti(P, Tr, w, h)
-    prm = api.default_params(max_slots=2, max_points=131072, max_rings=64, max_features=args.features, max_matches=args.features,
-                             icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
+    cal = pyoracle.Oracle().calib_from_kitti(P, Tr, w, h)
+    prm = pyoracle.default_params(max_slots=2, max_points=MAX_POINTS, max_rings=64, max_features=args.features, max_matches=args.features,
+                                  icp_skip=args.icp_skip, num_cams=4 if args.rig == 1 else 2)
     cores = os.cpu_count() or 1
     frames = cores                       # one frame pair per host thread (the CPU's best configuration): ~23 s per step on the 16-thread box
     times = []
@@ -290,12 +403,11 @@ def run_reference(args, rank, world):
     val = frames / sec
     out = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32 geometry/indices, f64 residuals+JtJ", "data": "synthetic",
-           "config": {"workload": "same per-frame schedule as the CUDA arm (ingest + 64 kd-trees, project+associate twice per camera, "
-                                  "6 ICP passes with icp_skip=%d, 2 visual assemblies); a step = %d frame pairs on %d host threads" % (args.icp_skip, frames, cores),
-                      "features_per_image": args.features, "icp_skip": args.icp_skip},
+           "dtype": DTYPE, "data": "synthetic",
+           "config": workload_config(args, world),
            "cpu_baseline": {"value": round(val, 4), "unit": "frames/s", "cores": cores, "kind": "port",
-                            "sample": f"{frames} frame pairs per step x {args.steps} steps, {cores} host threads"},
+                            "sample": f"a step = {frames} frame pairs of the workload (one per host thread, {cores} threads: ingest + 64 kd-trees, project+associate "
+                                      f"twice per camera, 6 ICP passes with icp_skip={args.icp_skip}, 2 visual assemblies) x {args.steps} steps"},
            "e2e": {"value": round(val, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -311,8 +423,13 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="frames per upload chunk of the end-to-end call (0 = library default: growing chunks)")
     ap.add_argument("--icp-ctas", type=int, default=0, help="CTAs per frame pair of the correspondence kernel (0 = library default)")
     ap.add_argument("--rig", type=int, default=0, help="0 = KITTI stereo, 1 = off-road 4-camera rig")
+    ap.add_argument("--pose-spread", default="tight", choices=["tight", "spec"],
+                    help="supplied ICP poses: tight = truth +- 0.004 rad / 0.04 m; spec = SURVEY 8(d): first pass from (0,0,0,0,0,1), then +- 0.02 rad / 0.05-0.2 m")
+    ap.add_argument("--scan-format", default="kitti", choices=["kitti", "xyz"], help="host scan records: KITTI float4 {x,y,z,reflectance} or packed xyz")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of two frames of the timed batch")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VELO_GPU_ABI_VERSION 1
+#define VELO_GPU_ABI_VERSION 2
 #define VELO_MAX_CAMS 4          /* kitti.h:4  num_cams_actual */
 #define VELO_NUM_KP_SETS 2       /* main.cpp:261 (after tracking) and main.cpp:600 (after detection) */
 #define VELO_NEQ 28              /* 21 upper-triangular JtJ + 6 Jtr + 1 cost */
@@ -185,6 +185,14 @@ int  velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int set, const f
 int  velo_gpu_icp_pass(velo_gpu_ctx *ctx, int slot_M, int slot_S, const double pose[6], int iter, int icp_skip,
                        velo_icp_corr *corr, int corr_capacity, int *n_queries, int *n_kept, double *neq);
 
+/* The same block for ALL ICP passes of one frameToFrame call (velo.h:616,800: f2f_iterations x icp_iterations passes) at
+ * supplied poses, in ONE launch of the fused kernel — the code path of the batched front end, where pass p+1 is seeded by the
+ * correspondences of pass p.  poses[n_passes][6], iters[n_passes] (the `iter` of velo.h:829 for each pass), n_passes <=
+ * max_icp_passes.  corr (nullable) receives the records of EVERY pass, [n_passes][corr_capacity]; neq [n_passes][VELO_NEQ_STRIDE].
+ * Seeding only changes the order in which candidates are visited: each pass equals velo_gpu_icp_pass at its pose, bit for bit. */
+int  velo_gpu_icp_passes(velo_gpu_ctx *ctx, int slot_M, int slot_S, const double *poses, const int *iters, int n_passes, int icp_skip,
+                         velo_icp_corr *corr, int corr_capacity, int *n_queries, double *neq);
+
 /* visual residual assembly of frameToFrame (velo.h:622-792) for all cameras at a supplied pose.
  * Frame1 = (slot1,set1) current, frame2 = (slot2,set2) previous: their keypoints / has_depth / kp_with_depth
  * are the device-resident results of velo_gpu_depth_assoc.  matches: per camera n_matches[c] pairs
@@ -239,7 +247,9 @@ int  velo_gpu_match_hamming(velo_gpu_ctx *ctx, const uint8_t *query, int n_query
 
 /* ---------------------------------------------------------------- batched path (throughput) */
 /* A batch is `count` consecutive slots starting at slot0.  Inputs are concatenated with fixed strides:
- *   scans   [count][max_points][4] float,   n_points[count]
+ *   scans   [count][max_points][4] float,   n_points[count]      (KITTI .bin records {x,y,z,reflectance}, kitti.h:142;
+ *           with scan_stride_floats == 3: [count][max_points][3], {x,y,z} only — loadPoints drops the reflectance anyway,
+ *           kitti.h:145-148 — a quarter less to move over PCIe; only n_points[i] records of a scan are copied either way)
  *   kp      [count][VELO_NUM_KP_SETS][num_cams][max_features][2] float, n_kp[count][sets][cams]
  *   matches [count][num_cams][max_matches][2] int, n_matches[count][cams]   (frame pair slot s / slot s-1)
  *   poses   [count][n_passes][6] double, pass_iter[n_passes]  (iter value of each ICP pass)
@@ -251,6 +261,7 @@ typedef struct velo_batch_inputs {
     const int    *matches;   const int *n_matches;
     const double *icp_poses; const int *pass_iter; int n_passes;
     const double *vis_poses; int n_vis_iters;
+    int scan_stride_floats;          /* 0 or 4: KITTI float4 records; 3: xyz records */
 } velo_batch_inputs;
 
 int  velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in);

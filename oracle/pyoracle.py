@@ -43,6 +43,23 @@ def build_ref(force=False):
     return br.build(force)
 
 
+def default_params(**kw):
+    """velo_gpu_params with the reference's tunables (kitti.h:3-35, main.cpp:42-49), filled here in plain Python so that the CPU
+    reference arm never loads the CUDA library."""
+    p = abi.Params()
+    p.num_cams, p.icp_skip, p.f2f_iterations, p.icp_iterations = 2, 200, 2, 3
+    p.enable_2d2d, p.enable_3d2d, p.abs_truncates = 1, 1, 0
+    p.weight_3D2D, p.weight_2D2D, p.weight_3DPD = 10.0, 500.0, 1.0
+    p.loss_thresh_3D2D, p.loss_thresh_2D2D, p.loss_thresh_3DPD, p.loss_thresh_3D3D = 0.01, 0.00002, 0.1, 0.04
+    p.depth_assoc_thresh, p.outlier_reject, p.correspondence_thresh_icp, p.icp_norm_condition = 0.015, 5.0, 0.5, 1e-5
+    p.max_slots, p.max_points, p.max_rings, p.max_features, p.max_matches, p.max_icp_passes = 4, 131072, 128, 3000, 3000, 6
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
 _P = C.c_void_p
 
 
@@ -231,8 +248,9 @@ class Oracle:
 
     # ---- timed CPU baseline
     def bench_frames(self, batch, prm, cal, threads, stages=abi.STAGE_ALL, want_out=False):
+        assert batch.scans.shape[-1] == 4, "the CPU reference reads KITTI float4 records (kitti.h:142)"
         bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
-                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis)
+                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis, 4)
         icp = np.zeros((batch.count, batch.n_passes, abi.NEQ_STRIDE)) if want_out else None
         vis = np.zeros((batch.count, batch.n_vis, abi.NEQ_STRIDE)) if want_out else None
         sec = self.lib.oracle_bench_frames(batch.count, threads, C.addressof(prm), C.addressof(cal), C.addressof(bi), stages, _ptr(icp), _ptr(vis))

@@ -617,3 +617,148 @@ def test_batched_triangulation(velo, oracle, calib, params, ctx):
     np.testing.assert_allclose(g2, o2, rtol=2e-6, atol=2e-6)
     e, _ = ctx.triangulate(np.zeros(1, np.int32), obs3[:0], np.zeros(1, np.int32), obs2[:0], poses)
     assert len(e) == 0
+
+
+# ------------------------------------------------------------------------------------------------ round 2: the benchmarked code path
+@pytest.mark.parametrize("spread", ["tight", "spec"])
+def test_fused_multipass_kernel_every_pass_vs_oracle(velo, oracle, calib, params, ctx, spread):
+    """The code path bench.py times: ONE launch of k_icp_pass for the 2 x 3 passes of a frame pair (velo.h:616,800), pass p+1
+    seeded by the correspondences of pass p, icp_skip = 1 on full scans (120k x 120k).  The records of EVERY pass are compared
+    with the oracle at that pass's pose: indices bit-exact, normals / plane points bit-exact, residual + Jacobian 1e-5,
+    normal equations 1e-4.  "spec" = SURVEY 8(d) poses: pass 0 from the reference's start (0,0,0,0,0,1) (main.cpp:170)."""
+    rawM, _ = velo.synth.scan(8)
+    rawS, _ = velo.synth.scan(7)
+    ctx.scan_upload(1, rawM); ctx.scan_upload(0, rawS)
+    ptsM, rsM, _ = oracle.segment(rawM, calib)
+    ptsS, rsS, _ = oracle.segment(rawS, calib)
+    iters = [p // params.icp_iterations + 1 for p in range(params.f2f_iterations * params.icp_iterations)]
+    poses = np.stack([velo.synth.pose_guess(8, p, spread=spread) for p in range(len(iters))])
+    corr, neq = ctx.icp_passes(1, 0, poses, iters, 1)
+    assert corr.shape[0] == len(iters) == 6
+    kept = []
+    for p, it in enumerate(iters):
+        ocorr, oneq, okept = oracle.icp_pass(ptsM, rsM, ptsS, rsS, poses[p], it, 1, params, 1)
+        assert corr.shape[1] == len(ocorr)
+        for f in ("src_ring", "src_idx", "kept", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
+            bad = np.nonzero(corr[p][f] != ocorr[f])[0]
+            assert len(bad) == 0, (p, f, len(bad), corr[p][bad[:3]], ocorr[bad[:3]])
+        k = ocorr["kept"] == 1
+        assert corr[p]["normal"][k].tobytes() == ocorr["normal"][k].tobytes() and corr[p]["v0"][k].tobytes() == ocorr["v0"][k].tobytes()
+        np.testing.assert_allclose(corr[p]["residual"][k], ocorr["residual"][k], rtol=RTOL_RES, atol=1e-9)
+        np.testing.assert_allclose(corr[p]["jacobian"][k], ocorr["jacobian"][k], rtol=RTOL_RES, atol=1e-9)
+        sc = np.abs(oneq[:56]).max()
+        np.testing.assert_allclose(neq[p, :56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
+        assert neq[p, 56] == oneq[56] == okept and neq[p, 58] == oneq[58]
+        kept.append(okept)
+        # and the single-pass entry point gives the same bits as the fused launch
+        if p in (0, 4):
+            c1, n1, _ = ctx.icp_pass(1, 0, poses[p], it, 1)
+            assert c1.tobytes() == corr[p].tobytes() and n1[:59].tobytes() == neq[p, :59].tobytes()
+    assert kept[0] > (50000 if spread == "tight" else 10000) and kept[-1] > 5000
+
+
+def test_bench_configuration_three_full_scans_vs_oracle(velo, oracle, calib):
+    """bench.py's configuration on 3 full scans (2 frame pairs): icp_skip = 1, 6 passes, 2000 features, batch_run and the one-call
+    batch_frontend vs the oracle's timed-baseline driver: block / query counts equal, H / g / cost within 1e-4."""
+    import os
+    prm = velo.api.default_params(max_slots=3, max_points=131072, max_rings=64, max_features=2000, max_matches=2000, icp_skip=1)
+    c = velo.api.Context(prm, calib)
+    try:
+        b = velo.synth.Batch(1000, 3, prm)
+        icp = np.zeros((3, b.n_passes, velo.abi.NEQ_STRIDE)); vis = np.zeros((3, b.n_vis, velo.abi.NEQ_STRIDE))
+        hd = np.zeros((3, 2, prm.num_cams, prm.max_features), np.int32); nh = np.zeros((3, 2, prm.num_cams), np.int32)
+        c.batch_frontend(0, b, 0, icp, vis, hd, nh)
+        c.batch_upload(0, b); c.batch_run(0, 3)
+        icp2 = np.zeros_like(icp); vis2 = np.zeros_like(vis)
+        c.batch_download(0, 3, icp2, vis2, None, None)
+        assert icp2[:, :, :59].tobytes() == icp[:, :, :59].tobytes() and vis2.tobytes() == vis.tobytes()
+        sec, oicp, ovis = oracle.bench_frames(b, prm, calib, threads=min(2, os.cpu_count() or 1), want_out=True)
+        for t in (1, 2):
+            for p in range(b.n_passes):
+                sc = np.abs(oicp[t, p, :56]).max()
+                np.testing.assert_allclose(icp[t, p, :56], oicp[t, p, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
+                assert icp[t, p, 56] == oicp[t, p, 56] and icp[t, p, 58] == oicp[t, p, 58] == b.n_points[t]
+            for it in range(b.n_vis):
+                sc = np.abs(ovis[t, it, :56]).max()
+                np.testing.assert_allclose(vis[t, it, :56], ovis[t, it, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
+                assert vis[t, it, 56] == ovis[t, it, 56] and vis[t, it, 57] == ovis[t, it, 57]
+        assert icp[1:, 0, 56].min() > 50000
+    finally:
+        c.close()
+
+
+def test_offroad_rig_visual_and_batched_path(velo, oracle, ctx4):
+    """BASELINE configs[3] end to end: 4 cameras x 8000 features.  (a) visual residual blocks (order, types, r, J) and normal
+    equations at C = 4 vs the oracle, iter 1 and 2; (b) the batched path at C = 4 (full front end per frame) vs the oracle's driver."""
+    cal = ctx4.cal
+    F = 8000
+    d = _visual_inputs(velo, oracle, cal, ctx4, F, 4, frames=(11, 12))
+    kpA0, _, _, hd0, kw0 = d[11]
+    _, kpB1, m1, hd1, kw1 = d[12]
+    matches = np.zeros((4, F, 2), np.int32); nm = np.zeros(4, np.int32); cat = []
+    for cam in range(4):
+        idx = np.nonzero(m1[cam])[0]
+        nm[cam] = len(idx); matches[cam, : len(idx), 0] = idx; matches[cam, : len(idx), 1] = idx
+        cat.append(matches[cam, : len(idx)])
+    cat = np.concatenate(cat)
+    prm4 = ctx4.prm
+    for it in (1, 2):
+        pose = velo.synth.pose_guess(12, 3 if it == 2 else 0)
+        ob, oneq = oracle.visual(kpB1, kpA0, hd1[1], hd0[0], kw1[1], kw0[0], nm, matches, cal, prm4, pose, it)
+        gb, gneq = ctx4.visual_residuals(1, 1, 0, 0, nm, cat, pose, it)
+        assert len(gb) == len(ob) > 4000 and set(np.unique(ob["cam"])) == {0, 1, 2, 3}
+        for f in ("cam", "match", "type", "n_res"):
+            assert np.array_equal(gb[f], ob[f]), f
+        np.testing.assert_allclose(gb["residual"], ob["residual"], rtol=RTOL_RES, atol=1e-12)
+        np.testing.assert_allclose(gb["jacobian"], ob["jacobian"], rtol=RTOL_RES, atol=1e-12)
+        np.testing.assert_allclose(gneq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max())
+        assert gneq[56] == oneq[56] and gneq[57] == oneq[57]
+    # (b) batched path, 4 cameras
+    prm = velo.api.default_params(max_slots=3, max_features=F, max_matches=F, num_cams=4, icp_skip=20, max_rings=64)
+    c = velo.api.Context(prm, cal)
+    try:
+        b = velo.synth.Batch(40, 3, prm, rig=1)
+        icp = np.zeros((3, b.n_passes, velo.abi.NEQ_STRIDE)); vis = np.zeros((3, b.n_vis, velo.abi.NEQ_STRIDE))
+        hd = np.zeros((3, 2, 4, F), np.int32); nh = np.zeros((3, 2, 4), np.int32)
+        c.batch_frontend(0, b, 0, icp, vis, hd, nh)
+        sec, oicp, ovis = oracle.bench_frames(b, prm, cal, threads=2, want_out=True)
+        for t in (1, 2):
+            for p in range(b.n_passes):
+                np.testing.assert_allclose(icp[t, p, :56], oicp[t, p, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oicp[t, p, :56]).max())
+                assert icp[t, p, 56] == oicp[t, p, 56] and icp[t, p, 58] == oicp[t, p, 58]
+            for it in range(b.n_vis):
+                np.testing.assert_allclose(vis[t, it, :56], ovis[t, it, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(ovis[t, it, :56]).max())
+                assert vis[t, it, 56] == ovis[t, it, 56] > 4000
+        pts, rs, _ = oracle.segment(b.scans[2, : b.n_points[2]], cal)
+        for cam in range(4):
+            rc, proj, valid = oracle.project(pts, rs, cal, cam)
+            for s in range(2):
+                ohd, _ = oracle.depth_assoc(valid, proj, rc, b.kp[2, s, cam])
+                assert np.array_equal(hd[2, s, cam], ohd) and nh[2, s, cam] == (ohd >= 0).sum()
+    finally:
+        c.close()
+
+
+def test_bad_inputs_are_errors_not_garbage(velo, calib, ctx):
+    """caller-supplied match indices outside their keypoint sets -> VELO_ERR_INVALID_ARG; a depth association on a slot whose scan
+    was replaced without projecting it again finds nothing (the old projection is void)"""
+    raw, _ = velo.synth.scan(7)
+    ctx.scan_upload(0, raw); ctx.scan_upload(1, raw)
+    kp = velo.synth.features(7, 500)[0][0]
+    for slot in (0, 1):
+        for cam in (0, 1):
+            ctx.project(slot, cam)
+            for s in (0, 1):
+                ctx.depth_assoc(slot, cam, kp, s)
+    nm = np.array([2, 0], np.int32)
+    ok = np.array([[0, 1], [2, 3]], np.int32)
+    ctx.visual_residuals(1, 1, 0, 0, nm, ok, np.zeros(6), 1)
+    for bad in ([[0, 500], [2, 3]], [[-1, 1], [2, 3]], [[0, 1], [1 << 20, 3]]):
+        with pytest.raises(velo.api.VeloError) as e:
+            ctx.visual_residuals(1, 1, 0, 0, nm, np.array(bad, np.int32), np.zeros(6), 1)
+        assert e.value.code == 3
+    hd, _ = ctx.depth_assoc(0, 0, kp, 0)
+    assert (hd >= 0).sum() > 50
+    ctx.scan_upload(0, raw)                      # new scan in the slot, not projected yet
+    hd, kw = ctx.depth_assoc(0, 0, kp, 0)
+    assert (hd >= 0).sum() == 0 and len(kw) == 0

@@ -18,7 +18,8 @@ SYNTH_LIB = os.path.join(HOST, "libvelo_synth.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off",   # host code decides calibration / pose constants bit for bit
+    "-shared", "-cudart", "static",
 ]
 
 

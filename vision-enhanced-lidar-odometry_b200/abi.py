@@ -1,7 +1,7 @@
 """ctypes mirror of include/velo_gpu.h (POD structs and constants)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CAMS = 4
 NUM_KP_SETS = 2
 NEQ = 28
@@ -71,6 +71,7 @@ class BatchInputs(C.Structure):
         ("matches", C.c_void_p), ("n_matches", C.c_void_p),
         ("icp_poses", C.c_void_p), ("pass_iter", C.c_void_p), ("n_passes", C.c_int),
         ("vis_poses", C.c_void_p), ("n_vis_iters", C.c_int),
+        ("scan_stride_floats", C.c_int),
     ]
 
 
@@ -95,7 +96,7 @@ EXPORTS = [
     "velo_gpu_device_name", "velo_gpu_host_alloc", "velo_gpu_host_free", "velo_gpu_timer_begin", "velo_gpu_timer_end",
     "velo_gpu_profile_enable", "velo_gpu_profile_reset", "velo_gpu_profile_read", "velo_gpu_kernel_name",
     "velo_gpu_scan_upload", "velo_gpu_scan_upload_rings", "velo_gpu_projection_upload", "velo_gpu_scan_info", "velo_gpu_scan_download", "velo_gpu_project",
-    "velo_gpu_project_download", "velo_gpu_depth_assoc", "velo_gpu_icp_pass", "velo_gpu_visual_residuals", "velo_gpu_frame_to_frame", "velo_gpu_match_hamming", "velo_gpu_triangulate",
+    "velo_gpu_project_download", "velo_gpu_depth_assoc", "velo_gpu_icp_pass", "velo_gpu_icp_passes", "velo_gpu_visual_residuals", "velo_gpu_frame_to_frame", "velo_gpu_match_hamming", "velo_gpu_triangulate",
     "velo_gpu_batch_upload", "velo_gpu_batch_run", "velo_gpu_batch_download", "velo_gpu_batch_frontend", "velo_gpu_launch_count",
     "velo_gpu_batch_counts",
 ]

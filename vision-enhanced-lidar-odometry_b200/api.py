@@ -56,6 +56,7 @@ def lib():
     L.velo_gpu_project_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]
     L.velo_gpu_depth_assoc.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]
     L.velo_gpu_icp_pass.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]
+    L.velo_gpu_icp_passes.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
     L.velo_gpu_visual_residuals.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
     L.velo_gpu_frame_to_frame.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]
     L.velo_gpu_match_hamming.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, C.POINTER(C.c_int), _P, _P]
@@ -275,6 +276,18 @@ class Context:
         self._ck(self.L.velo_gpu_icp_pass(self.h, slot_M, slot_S, _ptr(pose), it, skip, _ptr(corr), cap, C.byref(nq), C.byref(nk), _ptr(neq)))
         return (corr[:nq.value] if want_corr else None), neq, nk.value
 
+    def icp_passes(self, slot_M, slot_S, poses, iters, skip, want_corr=True):
+        """all ICP passes of a frame pair in one launch of the fused kernel; returns (corr[n_passes][nq] | None, neq[n_passes][64])"""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)
+        iters = np.ascontiguousarray(iters, np.int32)
+        n = len(iters)
+        cap = self.prm.max_points
+        corr = np.zeros((n, cap), abi.ICP_CORR_DTYPE) if want_corr else None
+        nq = C.c_int()
+        neq = np.zeros((n, abi.NEQ_STRIDE), np.float64)
+        self._ck(self.L.velo_gpu_icp_passes(self.h, slot_M, slot_S, _ptr(poses), _ptr(iters), n, skip, _ptr(corr), cap, C.byref(nq), _ptr(neq)))
+        return (corr[:, :nq.value] if want_corr else None), neq
+
     def visual_residuals(self, slot1, set1, slot2, set2, n_matches, matches, pose, it, lm_valid=None, lm_xyz=None):
         """matches: concatenated per camera, [sum(n_matches)][2]"""
         n_matches = np.ascontiguousarray(n_matches, np.int32)
@@ -332,7 +345,7 @@ class Context:
     # ---- batched path
     def batch_upload(self, slot0, batch):
         bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
-                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis)
+                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis, batch.scans.shape[-1])
         self._ck(self.L.velo_gpu_batch_upload(self.h, slot0, batch.count, C.addressof(bi)))
 
     def batch_run(self, slot0, count, stages=abi.STAGE_ALL, first_has_prev=0):
@@ -343,7 +356,7 @@ class Context:
 
     def batch_frontend(self, slot0, batch, chunk=0, icp_neq=None, vis_neq=None, has_depth=None, n_hits=None):
         bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
-                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis)
+                             _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis, batch.scans.shape[-1])
         self._ck(self.L.velo_gpu_batch_frontend(self.h, slot0, batch.count, C.addressof(bi), chunk, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
 
     def batch_counts(self, slot0, count):

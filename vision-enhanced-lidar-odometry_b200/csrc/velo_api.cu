@@ -15,7 +15,7 @@ static thread_local std::string g_create_error;
 struct ProfRec { int k; cudaEvent_t a, b; };
 
 struct velo_gpu_ctx {
-    int device = 0;
+    int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;   // stream2: every other chunk of batch_frontend
     cudaStream_t launch_stream = nullptr;                                        // stream of the launch being profiled
     std::vector<cudaEvent_t> chunk_ev;
@@ -29,6 +29,10 @@ struct velo_gpu_ctx {
     VisUnit *h_vis_units = nullptr, *d_vis_units = nullptr;
     double *d_icp_partial = nullptr, *d_icp_out = nullptr, *d_vis_partial = nullptr, *d_vis_out = nullptr;
     int icp_partial_ctas = 0, vis_ctas = 0;
+    // the single-frame entry points stage through their own unit / partial / out records (index S resp. S*V), never through the
+    // batch path's slot records
+    int icp_scratch = 0, vis_scratch = 0;
+    int *d_flags = nullptr;         // [0]: a visual match index was out of range
     int batch_passes = 0, batch_vis = 0;
     velo_icp_corr *d_corr = nullptr;
     VisMatchOut *d_mout = nullptr;
@@ -39,6 +43,7 @@ struct velo_gpu_ctx {
     // Hamming matcher scratch (grown on demand)
     unsigned long long *d_hq = nullptr, *d_ht = nullptr; int *d_hidx = nullptr, *d_hdist = nullptr; size_t ham_cap_q = 0, ham_cap_t = 0;
     std::vector<int> h_npoints;     // host copy of n_points per slot (single-frame path)
+    std::vector<int> h_stride;      // staging of raw_stride (must outlive the asynchronous copy)
     // timing
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool profile = false;
@@ -267,7 +272,7 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     if (cudaGetDeviceProperties(&dp, device) != cudaSuccess || dp.major != 10)
         return fail(nullptr, VELO_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
     ctx = new velo_gpu_ctx();
-    ctx->device = device; ctx->prm = *prm; ctx->cal = *cal;
+    ctx->device = device; ctx->prm = *prm; ctx->cal = *cal; ctx->sm_count = dp.multiProcessorCount;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); velo_gpu_destroy(ctx); return fail(nullptr, VELO_ERR_CUDA, m); } } while (0)
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -277,7 +282,7 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     B.S = prm->max_slots; B.N = (prm->max_points + 127) & ~127; B.R = prm->max_rings; B.C = prm->num_cams;
     B.F = prm->max_features; B.MM = prm->max_matches; B.P = prm->max_icp_passes;
     const size_t S = B.S, N = B.N, R = B.R, C = B.C, F = B.F, MM = B.MM, P = B.P;
-    CKC(dalloc(ctx, &B.raw, S * N)); CKC(dalloc(ctx, &B.flagbits, S * (N / 32)));
+    CKC(dalloc(ctx, &B.raw, S * N)); CKC(dalloc(ctx, &B.raw_stride, S)); CKC(dalloc(ctx, &B.flagbits, S * (N / 32)));
     CKC(dalloc(ctx, &B.n_points, S)); CKC(dalloc(ctx, &B.n_rings, S)); CKC(dalloc(ctx, &B.ring_start, S * (R + 1))); CKC(dalloc(ctx, &B.status, S));
     CKC(dalloc(ctx, &B.pts, S * N)); CKC(dalloc(ctx, &B.sorted, S * N));
     CKC(dalloc(ctx, &B.cell_start, S * R * (VELO_AZ_BINS + 1))); CKC(dalloc(ctx, &B.sec_box, S * R * VELO_SECTORS));
@@ -292,20 +297,22 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     // units / normal equations
     ctx->icp_partial_ctas = 296;
     if (prm->max_icp_passes > VELO_MAX_PASSES) { velo_gpu_destroy(ctx); return fail(nullptr, VELO_ERR_INVALID_ARG, "max_icp_passes exceeds VELO_MAX_PASSES (6)"); }
-    const size_t n_icp_units = S, n_vis_units = S * (size_t)(prm->f2f_iterations > 0 ? prm->f2f_iterations : 1);
+    const size_t n_vis_batch = S * (size_t)(prm->f2f_iterations > 0 ? prm->f2f_iterations : 1);
+    const size_t n_icp_units = S + 1, n_vis_units = n_vis_batch + 1;
+    ctx->icp_scratch = (int)S; ctx->vis_scratch = (int)n_vis_batch;
     CKC(cudaMallocHost((void **)&ctx->h_icp_units, n_icp_units * sizeof(IcpUnit)));
     CKC(cudaMallocHost((void **)&ctx->h_vis_units, n_vis_units * sizeof(VisUnit)));
     CKC(dalloc(ctx, &ctx->d_icp_units, n_icp_units)); CKC(dalloc(ctx, &ctx->d_vis_units, n_vis_units));
     const size_t part = n_icp_units * (size_t)launch_icp_runs_cap((int)N);     // one record per run of queries (velo_icp.cu)
-    CKC(dalloc(ctx, &ctx->d_icp_partial, part * VELO_MAX_PASSES * 64)); CKC(dalloc(ctx, &ctx->d_icp_out, S * P * VELO_NEQ_STRIDE));
+    CKC(dalloc(ctx, &ctx->d_icp_partial, part * VELO_MAX_PASSES * 64)); CKC(dalloc(ctx, &ctx->d_icp_out, n_icp_units * P * VELO_NEQ_STRIDE));
     ctx->vis_ctas = 0;
-    size_t vpart = n_vis_units * 4; if (vpart < 64) vpart = 64;
+    const size_t vpart = n_vis_batch * 4 + 64;      // batch: 4 CTAs per unit; scratch: up to 64
     CKC(dalloc(ctx, &ctx->d_vis_partial, vpart * 64)); CKC(dalloc(ctx, &ctx->d_vis_out, n_vis_units * VELO_NEQ_STRIDE));
-    CKC(dalloc(ctx, &ctx->d_corr, N)); CKC(dalloc(ctx, &ctx->d_mout, C * MM));
+    CKC(dalloc(ctx, &ctx->d_corr, N * P)); CKC(dalloc(ctx, &ctx->d_mout, C * MM)); CKC(dalloc(ctx, &ctx->d_flags, 4));
     CKC(dalloc(ctx, &ctx->d_lm_valid, C * MM)); CKC(dalloc(ctx, &ctx->d_lm_xyz, C * MM));
     CKC(dalloc(ctx, &ctx->d_lm, 1)); CKC(dalloc(ctx, &ctx->d_pose, 8)); CKC(dalloc(ctx, &ctx->d_eval_partial, (size_t)296 * 64));
     CKC(dalloc(ctx, &ctx->d_eval_out, VELO_NEQ_STRIDE)); CKC(dalloc(ctx, &ctx->d_zero_neq, VELO_NEQ_STRIDE)); CKC(dalloc(ctx, &ctx->d_sel, C * MM));
-    ctx->h_npoints.assign(S, 0);
+    ctx->h_npoints.assign(S, 0); ctx->h_stride.assign(S, 4);
     // calibration for the device
     DevCalib &d = ctx->dcal; memset(&d, 0, sizeof(d));
     for (int i = 0; i < 12; i++) d.vtc[i] = cal->velo_to_cam[i];
@@ -394,6 +401,9 @@ extern "C" int velo_gpu_scan_upload(velo_gpu_ctx *ctx, int slot, const float *xy
     const DevBuffers &B = ctx->B;
     if (n > 0) CK(cudaMemcpyAsync(B.raw + (size_t)slot * B.N, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(B.n_points + slot, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int four = 4;
+    CK(cudaMemcpyAsync(B.raw_stride + slot, &four, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(B.proj_count + (size_t)slot * B.C * B.R, 0, (size_t)B.C * B.R * sizeof(int), ctx->stream));   // projections of the old scan are void
     CK(cudaStreamSynchronize(ctx->stream)); // &n is a stack variable
     ctx->h_npoints[slot] = n;
     Launcher L = launcher(ctx);
@@ -420,6 +430,7 @@ extern "C" int velo_gpu_scan_upload_rings(velo_gpu_ctx *ctx, int slot, const flo
     CK(cudaMemcpyAsync(B.n_points + slot, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(B.n_rings + slot, &n_rings, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(B.status + slot, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(B.proj_count + (size_t)slot * B.C * B.R, 0, (size_t)B.C * B.R * sizeof(int), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->h_npoints[slot] = n;
     launch_index(launcher(ctx), B, ctx->dcal, slot, 1);
@@ -557,36 +568,63 @@ static void add_icp_pass(const velo_gpu_ctx *ctx, IcpUnit *u, const double pose[
 }
 static int auto_ctas(const velo_gpu_ctx *ctx, int n_units, int cap) {
     int c = ctx->prm.ctas_per_icp_unit;
-    if (c <= 0) { c = (148 * 6 * 10 + n_units - 1) / n_units; if (c < 8) c = 8; }   // ~10 waves of 6 CTAs/SM
+    if (c <= 0) { c = (ctx->sm_count * 6 * 10 + n_units - 1) / n_units; if (c < 8) c = 8; }   // ~10 waves of 6 CTAs/SM
     if (c > cap) c = cap;
     return c < 1 ? 1 : c;
+}
+
+// scratch records of the single-frame entry points (never the batch path's slot records)
+static IcpUnit *sc_h_icp(velo_gpu_ctx *c) { return c->h_icp_units + c->icp_scratch; }
+static IcpUnit *sc_d_icp(velo_gpu_ctx *c) { return c->d_icp_units + c->icp_scratch; }
+static double *sc_icp_partial(velo_gpu_ctx *c) { return c->d_icp_partial + (size_t)c->icp_scratch * launch_icp_runs_cap(c->B.N) * VELO_MAX_PASSES * 64; }
+static double *sc_icp_out(velo_gpu_ctx *c) { return c->d_icp_out + (size_t)c->icp_scratch * c->B.P * VELO_NEQ_STRIDE; }
+static VisUnit *sc_h_vis(velo_gpu_ctx *c) { return c->h_vis_units + c->vis_scratch; }
+static VisUnit *sc_d_vis(velo_gpu_ctx *c) { return c->d_vis_units + c->vis_scratch; }
+static double *sc_vis_partial(velo_gpu_ctx *c) { return c->d_vis_partial + (size_t)c->vis_scratch * 4 * 64; }
+static double *sc_vis_out(velo_gpu_ctx *c) { return c->d_vis_out + (size_t)c->vis_scratch * VELO_NEQ_STRIDE; }
+
+// one frame pair, n_passes supplied poses, ONE launch of the fused kernel (pass p+1 seeded by pass p) — the code path of the batch
+extern "C" int velo_gpu_icp_passes(velo_gpu_ctx *ctx, int slot_M, int slot_S, const double *poses, const int *iters, int n_passes, int icp_skip,
+                                   velo_icp_corr *corr, int corr_capacity, int *n_queries, double *neq) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot_M) || check_slot(ctx, slot_S)) return VELO_ERR_INVALID_ARG;
+    if (!poses || !iters || icp_skip < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "bad poses / iters / icp_skip");
+    if (n_passes < 1 || n_passes > ctx->B.P) return fail(ctx, VELO_ERR_CAPACITY, "n_passes exceeds max_icp_passes");
+    for (int p = 0; p < n_passes; p++) if (iters[p] < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "iter must be >= 1");
+    CK(cudaSetDevice(ctx->device));
+    int st = slot_status(ctx, slot_M); if (st) return st;
+    st = slot_status(ctx, slot_S); if (st) return st;
+    IcpUnit *u = sc_h_icp(ctx);
+    init_icp_unit(ctx, u, slot_M, slot_S, icp_skip);
+    for (int p = 0; p < n_passes; p++) add_icp_pass(ctx, u, poses + 6 * p, iters[p]);
+    CK(cudaMemcpyAsync(sc_d_icp(ctx), u, sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+    const int ctas = auto_ctas(ctx, 1, ctx->icp_partial_ctas);
+    // every query writes its record in every pass, so the records need no clearing
+    launch_icp(launcher(ctx), ctx->B, ctx->dcal, sc_d_icp(ctx), 1, n_passes, ctas, sc_icp_partial(ctx), sc_icp_out(ctx), ctx->B.P,
+               corr ? ctx->d_corr : nullptr, corr ? ctx->B.N : 0);
+    CK(cudaGetLastError());
+    std::vector<double> out((size_t)n_passes * VELO_NEQ_STRIDE);
+    CK(cudaMemcpyAsync(out.data(), sc_icp_out(ctx), out.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));     // also: the scratch unit is host memory reused by the next call
+    const int nq = (int)out[58];
+    if (corr) {
+        if (nq > corr_capacity) return fail(ctx, VELO_ERR_CAPACITY, "corr_capacity smaller than the number of queries");
+        if (nq > 0) CK(cudaMemcpy2DAsync(corr, (size_t)corr_capacity * sizeof(velo_icp_corr), ctx->d_corr, (size_t)ctx->B.N * sizeof(velo_icp_corr),
+                                         (size_t)nq * sizeof(velo_icp_corr), n_passes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_queries) *n_queries = nq;
+    if (neq) memcpy(neq, out.data(), out.size() * sizeof(double));
+    return VELO_OK;
 }
 
 extern "C" int velo_gpu_icp_pass(velo_gpu_ctx *ctx, int slot_M, int slot_S, const double pose[6], int iter, int icp_skip,
                                  velo_icp_corr *corr, int corr_capacity, int *n_queries, int *n_kept, double *neq) {
     if (!ctx) return VELO_ERR_INVALID_ARG;
-    if (check_slot(ctx, slot_M) || check_slot(ctx, slot_S)) return VELO_ERR_INVALID_ARG;
-    if (!pose || iter < 1 || icp_skip < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "bad pose / iter / icp_skip");
-    CK(cudaSetDevice(ctx->device));
-    int st = slot_status(ctx, slot_M); if (st) return st;
-    st = slot_status(ctx, slot_S); if (st) return st;
-    init_icp_unit(ctx, &ctx->h_icp_units[0], slot_M, slot_S, icp_skip);
-    add_icp_pass(ctx, &ctx->h_icp_units[0], pose, iter);
-    CK(cudaMemcpyAsync(ctx->d_icp_units, ctx->h_icp_units, sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
-    const int ctas = auto_ctas(ctx, 1, ctx->icp_partial_ctas);
-    if (corr) CK(cudaMemsetAsync(ctx->d_corr, 0, (size_t)ctx->B.N * sizeof(velo_icp_corr), ctx->stream));
-    launch_icp(launcher(ctx), ctx->B, ctx->dcal, ctx->d_icp_units, 1, 1, ctas, ctx->d_icp_partial, ctx->d_icp_out, 1, corr ? ctx->d_corr : nullptr);
-    CK(cudaGetLastError());
+    if (!pose || iter < 1) return fail(ctx, VELO_ERR_INVALID_ARG, "bad pose / iter");
     double out[VELO_NEQ_STRIDE];
-    CK(cudaMemcpyAsync(out, ctx->d_icp_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const int nq = (int)out[58];
-    if (corr) {
-        if (nq > corr_capacity) return fail(ctx, VELO_ERR_CAPACITY, "corr_capacity smaller than the number of queries");
-        if (nq > 0) CK(cudaMemcpyAsync(corr, ctx->d_corr, (size_t)nq * sizeof(velo_icp_corr), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    if (n_queries) *n_queries = nq;
+    const int rc = velo_gpu_icp_passes(ctx, slot_M, slot_S, pose, &iter, 1, icp_skip, corr, corr_capacity, n_queries, out);
+    if (rc) return rc;
     if (n_kept) *n_kept = (int)out[56];
     if (neq) memcpy(neq, out, sizeof(out));
     return VELO_OK;
@@ -624,21 +662,25 @@ extern "C" int velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1,
         off += n_matches[c];
     }
     CK(cudaMemcpyAsync(B.n_matches + (size_t)slot1 * C, n_matches, C * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    VisUnit *u = &ctx->h_vis_units[0];
+    VisUnit *u = sc_h_vis(ctx);
     memset(u, 0, sizeof(*u));
     u->slot1 = slot1; u->set1 = set1; u->slot2 = slot2; u->set2 = set2; u->iter = iter;
     memcpy(u->pose, pose, 6 * sizeof(double));
-    CK(cudaMemcpyAsync(ctx->d_vis_units, u, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(sc_d_vis(ctx), u, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_mout, 0, (size_t)C * MM * sizeof(VisMatchOut), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     const int ctas = 32;
-    launch_visual(launcher(ctx), B, ctx->dcal, ctx->d_vis_units, 1, vis_tun(ctx), lm_valid ? ctx->d_lm_valid : nullptr, lm_valid ? ctx->d_lm_xyz : nullptr,
-                  ctx->d_vis_partial, ctx->d_vis_out, ctx->d_mout, ctas);
+    launch_visual(launcher(ctx), B, ctx->dcal, sc_d_vis(ctx), 1, vis_tun(ctx), lm_valid ? ctx->d_lm_valid : nullptr, lm_valid ? ctx->d_lm_xyz : nullptr,
+                  sc_vis_partial(ctx), sc_vis_out(ctx), ctx->d_mout, ctas, VisFixed{ nullptr, nullptr, nullptr, nullptr }, ctx->d_flags);
     CK(cudaGetLastError());
     double out[VELO_NEQ_STRIDE];
-    CK(cudaMemcpyAsync(out, ctx->d_vis_out, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+    int bad = 0;
+    CK(cudaMemcpyAsync(out, sc_vis_out(ctx), sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&bad, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<VisMatchOut> mo((size_t)C * MM);
     CK(cudaMemcpyAsync(mo.data(), ctx->d_mout, mo.size() * sizeof(VisMatchOut), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(ctx, VELO_ERR_INVALID_ARG, "a match index is outside the keypoint set it refers to");
     // residualStats order: camera-major, match order, block order (velo.h:934-976)
     int nb = 0;
     for (int c = 0; c < C; c++) for (int i = 0; i < n_matches[c]; i++) {
@@ -689,23 +731,22 @@ extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, 
     velo_f2f_report rep; memset(&rep, 0, sizeof(rep));
     const int eval_ctas = 148, max_lm = 50;
     for (int iter = 1; iter <= F2F; iter++) {
-        VisUnit *vu = &ctx->h_vis_units[0];
+        VisUnit *vu = sc_h_vis(ctx);
         if (visual) {   // freeze the visual block list of this f2f iteration at the current transform (velo.h:622-792)
             memset(vu, 0, sizeof(*vu));
             vu->slot1 = slot_M; vu->set1 = set1; vu->slot2 = slot_S; vu->set2 = set2; vu->iter = iter;
             memcpy(vu->pose, transform, 6 * sizeof(double));
-            CK(cudaMemcpyAsync(ctx->d_vis_units, vu, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));     // h_vis_units[0] is rewritten below
-            launch_visual(L, B, ctx->dcal, ctx->d_vis_units, 1, tun, d_lmv, d_lmx, ctx->d_vis_partial, ctx->d_vis_out, nullptr, 32,
-                          VisFixed{ nullptr, ctx->d_sel, nullptr, nullptr });
+            CK(cudaMemcpyAsync(sc_d_vis(ctx), vu, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));     // the scratch unit is rewritten below
+            launch_visual(L, B, ctx->dcal, sc_d_vis(ctx), 1, tun, d_lmv, d_lmx, sc_vis_partial(ctx), sc_vis_out(ctx), nullptr, 32,
+                          VisFixed{ nullptr, ctx->d_sel, nullptr, nullptr }, ctx->d_flags);
         }
         for (int ii = 0; ii < ICP; ii++) {
             if (enable_icp) {   // freeze the ICP correspondences at the current transform (velo.h:806-894)
-                init_icp_unit(ctx, &ctx->h_icp_units[0], slot_M, slot_S, icp_skip);
-                add_icp_pass(ctx, &ctx->h_icp_units[0], transform, iter);
-                CK(cudaMemcpyAsync(ctx->d_icp_units, ctx->h_icp_units, sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaMemsetAsync(ctx->d_corr, 0, (size_t)B.N * sizeof(velo_icp_corr), ctx->stream));
-                launch_icp(L, B, ctx->dcal, ctx->d_icp_units, 1, 1, auto_ctas(ctx, 1, ctx->icp_partial_ctas), ctx->d_icp_partial, ctx->d_icp_out, 1, ctx->d_corr);
+                init_icp_unit(ctx, sc_h_icp(ctx), slot_M, slot_S, icp_skip);
+                add_icp_pass(ctx, sc_h_icp(ctx), transform, iter);
+                CK(cudaMemcpyAsync(sc_d_icp(ctx), sc_h_icp(ctx), sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+                launch_icp(L, B, ctx->dcal, sc_d_icp(ctx), 1, 1, auto_ctas(ctx, 1, ctx->icp_partial_ctas), sc_icp_partial(ctx), sc_icp_out(ctx), ctx->B.P, ctx->d_corr);
             }
             CK(cudaMemcpyAsync(ctx->d_pose, transform, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));     // `transform` / h_icp_units are host memory reused below
@@ -714,11 +755,12 @@ extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, 
             for (int ev = 0; ev <= max_lm && !hs.done; ) {
                 for (int k = 0; k < 4 && ev <= max_lm; k++, ev++) {   // a few controller steps per host look
                     if (visual)
-                        launch_visual(L, B, ctx->dcal, ctx->d_vis_units, 1, tun, d_lmv, d_lmx, ctx->d_vis_partial, ctx->d_vis_out, nullptr, 32,
+                        launch_visual(L, B, ctx->dcal, sc_d_vis(ctx), 1, tun, d_lmv, d_lmx, sc_vis_partial(ctx), sc_vis_out(ctx), nullptr, 32,
                                       VisFixed{ ctx->d_sel, nullptr, ctx->d_lm->xt_ptr(), ctx->d_lm->done_ptr() });
                     if (enable_icp)
-                        launch_icp_eval(L, B, ctx->d_corr, B.N, slot_M, ctx->d_lm, ctx->prm.loss_thresh_3DPD, ctx->prm.weight_3DPD, ctx->d_eval_partial, eval_ctas, ctx->d_eval_out);
-                    launch_lm_step(L, ctx->d_lm, enable_icp ? ctx->d_eval_out : ctx->d_zero_neq, visual ? ctx->d_vis_out : ctx->d_zero_neq);
+                        launch_icp_eval(L, B, ctx->d_corr, sc_icp_out(ctx) + 58 /* number of records the pass wrote */, slot_M, ctx->d_lm, ctx->prm.loss_thresh_3DPD,
+                                        ctx->prm.weight_3DPD, ctx->d_eval_partial, eval_ctas, ctx->d_eval_out);
+                    launch_lm_step(L, ctx->d_lm, enable_icp ? ctx->d_eval_out : ctx->d_zero_neq, visual ? sc_vis_out(ctx) : ctx->d_zero_neq);
                 }
                 CK(cudaMemcpyAsync(&hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
@@ -826,7 +868,7 @@ static int upload_range(velo_gpu_ctx *ctx, int slot0_all, int i0, int count, con
     velo_batch_inputs inl = *src, *in = &inl;
     {
         const size_t C_ = ctx->B.C, F_ = ctx->B.F, MM_ = ctx->B.MM, per_ = VELO_NUM_KP_SETS * C_;
-        if (inl.scans) inl.scans += (size_t)i0 * ctx->prm.max_points * 4;
+        if (inl.scans) inl.scans += (size_t)i0 * ctx->prm.max_points * (inl.scan_stride_floats == 3 ? 3 : 4);
         if (inl.n_points) inl.n_points += i0;
         if (inl.kp) inl.kp += (size_t)i0 * per_ * F_ * 2;
         if (inl.n_kp) inl.n_kp += (size_t)i0 * per_;
@@ -838,11 +880,20 @@ static int upload_range(velo_gpu_ctx *ctx, int slot0_all, int i0, int count, con
     const DevBuffers &B = ctx->B;
     const size_t C = B.C, F = B.F, MM = B.MM;
     if (in->scans && in->n_points) {
-        for (int i = 0; i < count; i++) if (in->n_points[i] < 0 || in->n_points[i] > ctx->prm.max_points) return fail(ctx, VELO_ERR_CAPACITY, "scan has more points than max_points");
-        CK(cudaMemcpy2DAsync(B.raw + (size_t)slot0 * B.N, (size_t)B.N * sizeof(float4), in->scans, (size_t)ctx->prm.max_points * sizeof(float4),
-                             (size_t)ctx->prm.max_points * sizeof(float4), count, cudaMemcpyHostToDevice, st));
+        if (in->scan_stride_floats != 0 && in->scan_stride_floats != 3 && in->scan_stride_floats != 4) return fail(ctx, VELO_ERR_INVALID_ARG, "scan_stride_floats must be 0, 3 or 4");
+        const size_t rec = (in->scan_stride_floats == 3 ? 3 : 4) * sizeof(float);
+        int nmax = 0;
+        for (int i = 0; i < count; i++) {
+            if (in->n_points[i] < 0 || in->n_points[i] > ctx->prm.max_points) return fail(ctx, VELO_ERR_CAPACITY, "scan has more points than max_points");
+            nmax = std::max(nmax, in->n_points[i]);
+        }
+        // one strided copy for the chunk; only the records the longest scan of the chunk has, not max_points per scan
+        if (nmax > 0) CK(cudaMemcpy2DAsync(B.raw + (size_t)slot0 * B.N, (size_t)B.N * sizeof(float4), in->scans, (size_t)ctx->prm.max_points * rec,
+                                           (size_t)nmax * rec, count, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(B.n_points + slot0, in->n_points, count * sizeof(int), cudaMemcpyHostToDevice, st));
-        for (int i = 0; i < count; i++) ctx->h_npoints[slot0 + i] = in->n_points[i];
+        for (int i = 0; i < count; i++) { ctx->h_npoints[slot0 + i] = in->n_points[i]; ctx->h_stride[slot0 + i] = (int)(rec / sizeof(float)); }
+        CK(cudaMemcpyAsync(B.raw_stride + slot0, ctx->h_stride.data() + slot0, count * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(B.proj_count + (size_t)slot0 * B.C * B.R, 0, (size_t)count * B.C * B.R * sizeof(int), st));   // projections of the old scans are void
     }
     if (in->kp && in->n_kp) {
         const size_t per = VELO_NUM_KP_SETS * C;
@@ -916,7 +967,8 @@ static int run_stages(velo_gpu_ctx *ctx, const Launcher &L, int slot0, int count
         const int n_units = pairs * V;
         if (skip_first) CK(cudaMemsetAsync(ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, 0, (size_t)V * VELO_NEQ_STRIDE * sizeof(double), st));
         launch_visual(L, B, ctx->dcal, ctx->d_vis_units + (size_t)s_first * V, n_units, vis_tun(ctx), nullptr, nullptr,
-                      ctx->d_vis_partial + (size_t)s_first * V * 4 * 64, ctx->d_vis_out + (size_t)s_first * V * VELO_NEQ_STRIDE, nullptr, 4);
+                      ctx->d_vis_partial + (size_t)s_first * V * 4 * 64, ctx->d_vis_out + (size_t)s_first * V * VELO_NEQ_STRIDE, nullptr, 4,
+                      VisFixed{ nullptr, nullptr, nullptr, nullptr }, ctx->d_flags);
     }
     CK(cudaGetLastError());
     return VELO_OK;
@@ -926,6 +978,7 @@ extern "C" int velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int s
     if (!ctx) return VELO_ERR_INVALID_ARG;
     if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (stages & VELO_STAGE_VISUAL) CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     return run_stages(ctx, launcher(ctx), slot0, count, stages, first_has_prev);
 }
 
@@ -940,8 +993,11 @@ extern "C" int velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, 
     if (vis_neq) CK(cudaMemcpyAsync(vis_neq, ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, (size_t)count * V * VELO_NEQ_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (has_depth) CK(cudaMemcpyAsync(has_depth, B.has_depth + (size_t)slot0 * per * B.F, (size_t)count * per * B.F * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (n_hits) CK(cudaMemcpyAsync(n_hits, B.n_hits + (size_t)slot0 * per, (size_t)count * per * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    int bad = 0;
+    if (vis_neq) CK(cudaMemcpyAsync(&bad, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
+    if (bad) return fail(ctx, VELO_ERR_INVALID_ARG, "a match index is outside the keypoint set it refers to");
     return VELO_OK;
 }
 
@@ -961,6 +1017,7 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
     const int nchunks = (int)cut.size() - 1;
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while ((int)ctx->chunk_ev.size() < nchunks + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     // the copy stream must not overwrite slots that earlier work on the compute stream may still read
     CK(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));

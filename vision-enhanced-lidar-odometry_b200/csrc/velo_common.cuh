@@ -20,7 +20,7 @@ __device__ __forceinline__ float d2f_xy2(const float4 &a, u64 mxy, float bz) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(pack2f(a.x, a.y)), "l"(mxy));
     asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(dxy));
     asm("mov.b64 {%0,%1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sq));
-    const float dz = __fsub_rn(a.z, bz);
+    const float dz = __fsub_rn(SORTED_Z(a), bz);
     return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
 }
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {

@@ -3,7 +3,7 @@
 // Layout in HBM (one context = one GPU).  S = max_slots, N = max_points (padded to 128), R = max_rings,
 // C = num_cams, F = max_features, MM = max_matches.  Everything is a dense [slot][...] array so that one
 // launch covers a whole batch of frames (grid.y / grid.z = slot):
-//   raw        float4 [S][N]          KITTI {x,y,z,reflectance} as uploaded            (kitti.h:121-152)
+//   raw        float4 [S][N]          KITTI {x,y,z,reflectance} as uploaded            (kitti.h:121-152); or packed {x,y,z} records (raw_stride = 3)
 //   flagbits   u32    [S][N/32]       ring-boundary flags (kitti.h:166)
 //   ring_start int    [S][R+1]        ring r = pts[ring_start[r] .. ring_start[r+1])
 //   pts        float4 [S][N]          ring-ordered cam-0 frame {x,y,z,1}               (kitti.h:154-185)
@@ -36,6 +36,15 @@
 #ifndef VELO_RG_MANT_BITS
 #define VELO_RG_MANT_BITS 6         /* measured 4/5/6 bits: 24.4 / 23.6 / 23.2 ms per 200 pairs x 6 passes */
 #endif
+// record of `sorted`: {x, y, z, index in ring}; with ICP_MIN_F64 {x, y, index, z}, so that the candidate key (index | d2 << 32) forms in
+// the aligned register pair the 16-byte load delivered
+#ifdef ICP_MIN_F64
+#define SORTED_IDX(c) ((c).z)
+#define SORTED_Z(c) ((c).w)
+#else
+#define SORTED_IDX(c) ((c).w)
+#define SORTED_Z(c) ((c).z)
+#endif
 #define VELO_IDX_BITS 20            /* index-in-ring bits of the neighbour key */
 #define VELO_RING_BITS 12
 
@@ -56,7 +65,7 @@ struct DevCalib {
 
 struct DevBuffers {
     int S, N, R, C, F, MM, P;
-    float4 *raw; uint32_t *flagbits; int *n_points; int *n_rings; int *ring_start; int *status;
+    float4 *raw; int *raw_stride; uint32_t *flagbits; int *n_points; int *n_rings; int *ring_start; int *status;   // raw_stride[S]: floats per uploaded record (4 = KITTI, 3 = xyz)
     float4 *pts; float4 *sorted; int *cell_start; float4 *sec_box;
     unsigned long long *mask_lo, *mask_hi; int W;   // [S][SEC][EL_BUCKETS][W]: rings with bucket(elev lo) <= b / bucket(elev hi) >= b
     unsigned long long *rmask_lo, *rmask_hi;        // [S][SEC][RG_BUCKETS][W]: the same over range buckets
@@ -136,16 +145,16 @@ void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, i
 void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams);
 // units: device array [n_units]; partial: [n_units][launch_icp_runs_cap(B.N)][VELO_MAX_PASSES][64] doubles; out: [n_units][out_stride_passes][VELO_NEQ_STRIDE];
-// corr optional (single unit, records of its last pass)
+// corr optional (single unit): records of its last pass, or with corr_stride > 0 of every pass ([pass][corr_stride])
 int launch_icp_runs_cap(int max_points);
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
-                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr);
+                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride = 0);
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
                    const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas,
-                   VisFixed fx = VisFixed{ nullptr, nullptr, nullptr, nullptr });
+                   VisFixed fx = VisFixed{ nullptr, nullptr, nullptr, nullptr }, int *bad_flag = nullptr);
 
 void launch_lm_init(const Launcher &L, LmState *S, const double *d_pose, int max_iterations);
-void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, int cap, int src_slot, const LmState *S,
+void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, const double *n_records, int src_slot, const LmState *S,
                      double loss_a, double weight, double *partial, int ctas, double *out);
 void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const double *e_vis);
 void launch_hamming(const Launcher &L, const unsigned long long *q, int nq, const unsigned long long *t, int nt, int words, int *best_idx, int *best_dist);

@@ -16,10 +16,15 @@ __global__ void __launch_bounds__(256) k_ingest_flags(DevBuffers B, int slot0) {
     if ((int)(blockIdx.x * blockDim.x) >= n) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const float4 *raw = B.raw + (size_t)slot * B.N;
+    const float *rawf = reinterpret_cast<const float *>(raw);
+    const int st = B.raw_stride[slot];
     float x = 0.f, y = 0.f;
-    if (i < n) { float2 xy = *reinterpret_cast<const float2 *>(raw + i); x = xy.x; y = xy.y; }
+    if (i < n) {
+        if (st == 4) { float2 xy = *reinterpret_cast<const float2 *>(raw + i); x = xy.x; y = xy.y; }
+        else { x = rawf[3 * (size_t)i]; y = rawf[3 * (size_t)i + 1]; }
+    }
     float py = __shfl_up_sync(FULL, y, 1);
-    if (lane == 0 && i > 0 && i < n) py = raw[i - 1].y;
+    if (lane == 0 && i > 0 && i < n) py = rawf[(size_t)st * (i - 1) + 1];
     bool f = (i > 0) && (i < n) && (x > 0.f) && ((y > 0.f) != (py > 0.f));
     unsigned m = __ballot_sync(FULL, f);
     if (lane == 0 && i < n) B.flagbits[(size_t)slot * (B.N / 32) + (i >> 5)] = m;
@@ -72,7 +77,9 @@ __global__ void __launch_bounds__(256) k_ingest_permute(DevBuffers B, DevCalib c
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_rs[mid] <= d) lo = mid; else hi = mid - 1; }
     const int r0 = s_rs[lo], L = s_rs[lo + 1] - r0, i = d - r0;
     const int src = r0 + (L - 1 - (i + L / 2) % L);
-    const float4 p = __ldg(B.raw + (size_t)slot * B.N + src);
+    float4 p;
+    if (B.raw_stride[slot] == 4) p = __ldg(B.raw + (size_t)slot * B.N + src);
+    else { const float *q = reinterpret_cast<const float *>(B.raw + (size_t)slot * B.N) + 3 * (size_t)src; p = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f); }
     float4 o;
     o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cal.vtc[0], p.x), __fmul_rn(cal.vtc[1], p.y)), __fmul_rn(cal.vtc[2], p.z)), cal.vtc[3]);
     o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cal.vtc[4], p.x), __fmul_rn(cal.vtc[5], p.y)), __fmul_rn(cal.vtc[6], p.z)), cal.vtc[7]);
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
         float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
         int b = az_bin(atan2f(vy, vx));
         int pos = s_hist[b] + atomicAdd(&s_cur[b], 1);
-        p.w = __int_as_float(i);
+        SORTED_Z(p) = p.z; SORTED_IDX(p) = __int_as_float(i);     // (z first: with ICP_MIN_F64 the index takes its place)
         sorted[pos] = p;
     }
 }

@@ -14,7 +14,7 @@
 
 // ------------------------------------------------------------------------------------------------ fixed 3DPD blocks
 // one thread per correspondence record of the last ICP pass (kept == 1 => a cost3DPD block with p, n, o frozen)
-__global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo_icp_corr *__restrict__ corr, int cap, int src_slot,
+__global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo_icp_corr *__restrict__ corr, const double *__restrict__ n_records, int src_slot,
                                                         const double *__restrict__ pose, const int *__restrict__ done,
                                                         double loss_a, double weight, double *__restrict__ partial) {
     __shared__ double s_rows[8][NEQ_STAGE];
@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo
     for (int i = 0; i < 6; i++) { x[i] = dj(pose[i]); x[i].v[i] = 1.0; }
     double acc = 0.0, raw = 0.0;
     int nk = 0;
+    const int cap = min(B.N, max(0, (int)*n_records));      // the records the correspondence pass wrote (its query count)
     const int per = (((cap + gridDim.x - 1) / gridDim.x) + 31) & ~31;
     const int q0 = blockIdx.x * per, q1 = min(cap, q0 + per);
     for (int qb = q0; qb < q1; qb += blockDim.x) {
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo
         if (q < q1) {
             const velo_icp_corr c = corr[q];
             if (c.kept == 1) {
+                // (src_ring, src_idx) were written by k_icp_pass for this source slot: in range by construction
                 const float4 p = pts[rs[c.src_ring] + c.src_idx];
                 const double k[9] = { p.x, p.y, p.z, c.normal[0], c.normal[1], c.normal[2], c.v0[0], c.v0[1], c.v0[2] };
                 DJ r[1];
@@ -166,10 +168,10 @@ void launch_lm_init(const Launcher &L, LmState *S, const double *d_pose, int max
     k_lm_init<<<1, 32, 0, L.stream>>>(S, d_pose, max_iterations);
     if (L.post) L.post(L.user, VK_SOLVE);
 }
-void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, int cap, int src_slot, const LmState *S,
+void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, const double *n_records, int src_slot, const LmState *S,
                      double loss_a, double weight, double *partial, int ctas, double *out) {
     if (L.pre) L.pre(L.user, VK_SOLVE);
-    k_icp_eval_fixed<<<ctas, 256, 0, L.stream>>>(B, corr, cap, src_slot, S->xt_ptr(), S->done_ptr(), loss_a, weight, partial);
+    k_icp_eval_fixed<<<ctas, 256, 0, L.stream>>>(B, corr, n_records, src_slot, S->xt_ptr(), S->done_ptr(), loss_a, weight, partial);
     k_eval_reduce<<<1, 64, 0, L.stream>>>(partial, ctas, out, S->done_ptr());
     if (L.post) L.post(L.user, VK_SOLVE);
 }

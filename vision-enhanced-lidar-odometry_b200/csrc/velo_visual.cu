@@ -20,7 +20,7 @@ __device__ __forceinline__ void take(Blk &o, int type, int nres, const DJ *r) {
 // grid = (ctas, n_units); threads stride over the (camera, match) pairs of the unit
 __global__ void __launch_bounds__(VIS_THREADS) k_visual(DevBuffers B, DevCalib cal, const VisUnit *__restrict__ units, VisTun tn,
                                                         const int *__restrict__ lm_valid, const float4 *__restrict__ lm_xyz,
-                                                        double *__restrict__ partial, VisMatchOut *__restrict__ mout, VisFixed fx) {
+                                                        double *__restrict__ partial, VisMatchOut *__restrict__ mout, VisFixed fx, int *__restrict__ bad_flag) {
     __shared__ double s_rows[VIS_THREADS / 32][NEQ_STAGE];
     __shared__ double s_red[(VIS_THREADS / 32) * 56];
     __shared__ int s_cnt[2];
@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(VIS_THREADS) k_visual(DevBuffers B, DevCalib c
             const size_t s1 = ((size_t)U.slot1 * VELO_NUM_KP_SETS + U.set1) * B.C + cam, s2 = ((size_t)U.slot2 * VELO_NUM_KP_SETS + U.set2) * B.C + cam;
             const int *mt = B.matches + 2 * (((size_t)U.slot1 * B.C + cam) * MM + i);
             const int p1 = mt[0], p2 = mt[1];
+            // caller-supplied indices: a pair that points outside its keypoint set adds no block and raises the error flag
+            const bool in_range = (unsigned)p1 < (unsigned)B.n_kp[s1] && (unsigned)p2 < (unsigned)B.n_kp[s2];
+            if (!in_range && bad_flag) atomicOr(bad_flag, 1);
+            if (in_range) {
             const int h1 = B.has_depth[s1 * B.F + p1], h2 = B.has_depth[s2 * B.F + p2];
             bool d1 = h1 != -1, d2 = h2 != -1;                                     // velo.h:631-632
             float4 q1 = make_float4(0, 0, 0, 0), q2 = make_float4(0, 0, 0, 0);
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(VIS_THREADS) k_visual(DevBuffers B, DevCalib c
                     for (int q = 0; q < 18; q++) vb.jacobian[q] = q < 6 * blk[b].nres ? blk[b].J[q] : 0.0;
                 }
             }
+            }
         }
         for (int b = 0; b < 3; b++) {
             for (int row = 0; row < 3; row++) {
@@ -132,11 +137,11 @@ __global__ void k_neq_reduce_vis(const double *__restrict__ partial, double *__r
 }
 
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
-                   const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas, VisFixed fx) {
+                   const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas, VisFixed fx, int *bad_flag) {
     if (n_units <= 0) return;
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_VISUAL);
-    k_visual<<<g, VIS_THREADS, 0, L.stream>>>(B, cal, units, tun, lm_valid, lm_xyz, partial, match_out, fx);
+    k_visual<<<g, VIS_THREADS, 0, L.stream>>>(B, cal, units, tun, lm_valid, lm_xyz, partial, match_out, fx, bad_flag);
     if (L.post) L.post(L.user, VK_VISUAL);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);
     k_neq_reduce_vis<<<n_units, 64, 0, L.stream>>>(partial, out, ctas);

@@ -233,6 +233,19 @@ void velo_synth_pose_guess(uint64_t seed, int frame, int pass, double out[6]) {
     for (int i=3;i<6;i++) out[i] += syn_sym(&r, 0.04) * s;
 }
 
+/* the same with a selectable spread.  spread 0: the tight guesses above.  spread 1 ("spec"): pass 0 is the
+ * reference's own start (0,0,0,0,0,1) (main.cpp:170); pass p >= 1 is the truth + w ~ U(+-0.02 rad)^3, t ~ (U(+-0.05), U(+-0.05),
+ * U(+-0.2)) m, shrinking 1/(1+p) like solver iterates do. */
+void velo_synth_pose_guess_spread(uint64_t seed, int frame, int pass, int spread, double out[6]) {
+    if (spread == 0) { velo_synth_pose_guess(seed, frame, pass, out); return; }
+    if (pass == 0) { out[0] = out[1] = out[2] = out[3] = out[4] = 0.0; out[5] = 1.0; return; }
+    velo_synth_pose(seed, frame, out);
+    syn_rng r = syn_seed(seed, 41 + (uint64_t)pass, (uint64_t)frame);
+    double s = 1.0 / (double)(1 + pass);
+    for (int i=0;i<3;i++) out[i] += syn_sym(&r, 0.02) * s;
+    out[3] += syn_sym(&r, 0.05) * s; out[4] += syn_sym(&r, 0.05) * s; out[5] += syn_sym(&r, 0.2) * s;
+}
+
 /* ---------------- lidar scan ---------------- */
 static double syn_elev_deg(int k) { return k < 32 ? 2.0 - k/3.0 : -8.83 - (k-32)/2.0; }
 

@@ -19,6 +19,7 @@ def lib():
         _lib.velo_synth_features.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.velo_synth_pose.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
         _lib.velo_synth_pose_guess.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        _lib.velo_synth_pose_guess_spread.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -55,9 +56,14 @@ def pose(frame, seed=SEED):
     return out
 
 
-def pose_guess(frame, pass_idx, seed=SEED):
+POSE_SPREADS = {"tight": 0, "spec": 1}
+
+
+def pose_guess(frame, pass_idx, seed=SEED, spread="tight"):
+    """supplied pose of ICP pass `pass_idx`.  "tight": truth +- 0.004 rad / 0.04 m, shrinking 1/(1+pass).  "spec" (SURVEY.md 8(d)):
+    pass 0 = the reference's start (0,0,0,0,0,1) (main.cpp:170), later passes truth +- 0.02 rad / (0.05, 0.05, 0.2) m, shrinking."""
     out = np.zeros(6, np.float64)
-    lib().velo_synth_pose_guess(seed, frame, pass_idx, out.ctypes.data)
+    lib().velo_synth_pose_guess_spread(seed, frame, pass_idx, POSE_SPREADS[spread], out.ctypes.data)
     return out
 
 
@@ -67,7 +73,7 @@ class Batch:
     `count` scans: frames frame0 .. frame0+count-1.  Frame pairs (t, t-1) exist for t >= 1 (slot 0 is the halo).
     Arrays may be views of pinned memory (pass `alloc`)."""
 
-    def __init__(self, frame0, count, prm, rig=0, seed=SEED, alloc=None, threads=None):
+    def __init__(self, frame0, count, prm, rig=0, seed=SEED, alloc=None, threads=None, pose_spread="tight"):
         C_, F, NP, MM = prm.num_cams, prm.max_features, prm.max_points, prm.max_matches
         n_passes = prm.f2f_iterations * prm.icp_iterations
         n_vis = prm.f2f_iterations
@@ -99,11 +105,28 @@ class Batch:
                 self.matches[i, c, :len(idx), 0] = idx
                 self.matches[i, c, :len(idx), 1] = idx
             for p in range(n_passes):
-                self.icp_poses[i, p] = pose_guess(fr, p, seed)
+                self.icp_poses[i, p] = pose_guess(fr, p, seed, pose_spread)
             for it in range(n_vis):
-                self.vis_poses[i, it] = pose_guess(fr, it * prm.icp_iterations, seed)
+                self.vis_poses[i, it] = pose_guess(fr, it * prm.icp_iterations, seed, pose_spread)
 
         import os
         nt = threads or min(32, os.cpu_count() or 1)
         with ThreadPoolExecutor(nt) as ex:
             list(ex.map(gen, range(count)))
+
+    def xyz(self, alloc=None):
+        """the same batch with packed {x,y,z} scan records (velo_batch_inputs.scan_stride_floats = 3)"""
+        v = self.view(0, self.count)
+        mk = alloc if alloc is not None else (lambda shape, dt: np.zeros(shape, dt))
+        v.scans = mk(self.scans.shape[:-1] + (3,), np.float32)
+        v.scans[...] = self.scans[..., :3]
+        return v
+
+    def view(self, first, count):
+        """entries [first, first + count) as a batch of their own (arrays are views; entry `first` becomes the halo scan)"""
+        v = object.__new__(Batch)
+        v.count, v.frame0 = count, self.frame0 + first
+        for k in ("scans", "n_points", "kp", "n_kp", "matches", "n_matches", "icp_poses", "vis_poses"):
+            setattr(v, k, getattr(self, k)[first:first + count])
+        v.pass_iter, v.n_passes, v.n_vis = self.pass_iter, self.n_passes, self.n_vis
+        return v

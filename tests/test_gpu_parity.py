@@ -762,3 +762,23 @@ def test_bad_inputs_are_errors_not_garbage(velo, calib, ctx):
     ctx.scan_upload(0, raw)                      # new scan in the slot, not projected yet
     hd, kw = ctx.depth_assoc(0, 0, kp, 0)
     assert (hd >= 0).sum() == 0 and len(kw) == 0
+
+
+def test_xyz_scan_records_equal_kitti_records(velo, calib):
+    """velo_batch_inputs.scan_stride_floats = 3 (packed xyz, a quarter less to upload; loadPoints drops the reflectance anyway,
+    kitti.h:145-148): every output of the batched front end is byte-identical to the KITTI float4 upload."""
+    prm = velo.api.default_params(max_slots=3, max_features=600, max_matches=600, icp_skip=7, max_rings=64)
+    c = velo.api.Context(prm, calib)
+    try:
+        b = velo.synth.Batch(50, 3, prm)
+        outs = []
+        for bb in (b, b.xyz()):
+            icp = np.zeros((3, b.n_passes, velo.abi.NEQ_STRIDE)); vis = np.zeros((3, b.n_vis, velo.abi.NEQ_STRIDE))
+            hd = np.zeros((3, 2, prm.num_cams, prm.max_features), np.int32); nh = np.zeros((3, 2, prm.num_cams), np.int32)
+            c.batch_frontend(0, bb, 0, icp, vis, hd, nh)
+            pts, rs = c.scan_download(2)
+            outs.append((icp.tobytes(), vis.tobytes(), hd.tobytes(), nh.tobytes(), pts.tobytes(), rs.tobytes()))
+            assert icp[1:, :, 56].min() > 1000 and vis[1:, :, 56].min() > 100
+        assert outs[0] == outs[1]
+    finally:
+        c.close()

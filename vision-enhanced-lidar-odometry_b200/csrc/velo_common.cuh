@@ -20,7 +20,7 @@ __device__ __forceinline__ float d2f_xy2(const float4 &a, u64 mxy, float bz) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(pack2f(a.x, a.y)), "l"(mxy));
     asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(dxy));
     asm("mov.b64 {%0,%1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sq));
-    const float dz = __fsub_rn(SORTED_Z(a), bz);
+    const float dz = __fsub_rn(a.z, bz);
     return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
 }
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -88,48 +88,49 @@ __device__ __forceinline__ int az_bin(float az) {
 
 
 // ------------------------------------------------------------------------------------------------ a13: normal equations
-// Row staging for the warp-cooperative accumulation of  H += rho' J^T J,  g += rho' J^T r,  cost += rho/2
-// (what ceres::Solve forms for the single 6-vector block, velo.h:897-902).
-// Each lane deposits one residual ROW {J[6], r, rho', rho/2 (only on the first row of a block), valid flag} component-major
-// (stride 33 doubles: conflict-free for the deposit and for the walk).  Lane l then walks the deposited rows in lane order with
-// the same three loads + DMUL/DADD/DFMA whatever it owns: fixed order => run-to-run deterministic.  Lane l < 27 owns H/g sum l
-// (robust in acc, unweighted in raw); lane 27 owns acc = sum of rho/2; lane 28 owns raw = sum of r^2 (the unweighted cost is
-// half of it, see neq_store).  (k_icp_pass, where this reduction is 15 % of the kernel, uses the FP64 tensor pipe instead.)
-#define NEQ_COMP 10
-#define NEQ_CS 33
-#define NEQ_STAGE (NEQ_COMP * NEQ_CS)                 /* doubles of the per-warp staging area (s_rows[warps][NEQ_STAGE]) */
-static __constant__ int c_pa[32] = { 0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5,  0,1,2,3,4,5, 8, 6, 0,0,0 };
-static __constant__ int c_pb[32] = { 0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5,  6,6,6,6,6,6, 9, 6, 0,0,0 };
+// H += rho' J^T J,  g += rho' J^T r,  cost += rho/2  — what ceres::Solve forms for the single 6-vector block (velo.h:897-902;
+// SURVEY.md A.3), robustified and unweighted.
+#define NEQ_STAGE (9 * 36 + 6)                        /* doubles of the per-warp staging area (s_rows[warps][NEQ_STAGE]) */
 
-__device__ __forceinline__ void warp_accum(double *s_rows, const double J[6], double r, double rho1, double rho0h, bool valid,
-                                           int lane, double &acc, double &raw) {
+// On the FP64 tensor pipe (the form k_icp_pass uses inline): X^T W X of one residual row per lane, X = [J, r, 0]
+// (8 columns), as eight m8n8k4 steps; a lane reads ONE staged element per step — it is both its A and its B fragment entry — plus the
+// row weight.  S = per-warp staging (>= 9 * 36 doubles).  The lane's accumulator fragments persist across calls: lane (fr, fk) =
+// (lane >> 2, lane & 3) holds C[fr][2 fk] and C[fr][2 fk + 1] of the raw (cr) and the weighted (cw) product.  Fixed order => deterministic.
+__device__ __forceinline__ void neq_mma_rows(double *S, int lane, const double J[6], double res, double wgt, bool valid,
+                                             double &cr0, double &cr1, double &cw0, double &cw1) {
     __syncwarp();
-    if (valid) {
-        double *row = s_rows + lane;
 #pragma unroll
-        for (int i = 0; i < 6; i++) row[i * NEQ_CS] = J[i];
-        row[6 * NEQ_CS] = r; row[7 * NEQ_CS] = rho1; row[8 * NEQ_CS] = rho0h; row[9 * NEQ_CS] = 1.0;
-    }
+    for (int c = 0; c < 6; c++) S[c * 36 + lane] = valid ? J[c] : 0.0;
+    S[6 * 36 + lane] = valid ? res : 0.0; S[7 * 36 + lane] = 0.0; S[8 * 36 + lane] = valid ? wgt : 0.0;
     __syncwarp();
-    const double *pa = s_rows + c_pa[lane] * NEQ_CS, *pb = s_rows + c_pb[lane] * NEQ_CS, *pw = s_rows + (lane == 27 ? 9 : 7) * NEQ_CS;
-    for (unsigned m = __ballot_sync(FULL, valid); m; m &= m - 1) {
-        const int i = __ffs(m) - 1;
-        const double p = pa[i] * pb[i];
-        raw += p;
-        acc = fma(pw[i], p, acc);                   // explicit fma: the sums are not parity-critical (1e-4)
+    const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const double x = S[fr * 36 + 4 * t + fk], w = S[8 * 36 + 4 * t + fk];
+        const double xw = x * w;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cr0), "+d"(cr1) : "d"(x), "d"(x));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cw0), "+d"(cw1) : "d"(x), "d"(xw));
     }
 }
-// where lane `lane`'s (acc, raw) go in a 56-slot record {28 robust, 28 unweighted}
-__device__ __forceinline__ void neq_store(double *rec56, int lane, double acc, double raw, bool add) {
-    if (lane < 28) rec56[lane] = (add ? rec56[lane] : 0.0) + acc;
-    if (lane < 27) rec56[28 + lane] = (add ? rec56[28 + lane] : 0.0) + raw;
-    if (lane == 28) rec56[55] = (add ? rec56[55] : 0.0) + 0.5 * raw;
+// the warp's fragments -> a 56-slot record {H upper row-major 21, g 6, cost | the same unweighted}; cost_half = the warp's sum of rho/2
+// (valid in every lane).  rec56 must be zero beforehand; every slot is written by exactly one lane.
+__device__ __forceinline__ void neq_mma_store(double *rec56, int lane, double cr0, double cr1, double cw0, double cw1, double cost_half) {
+    const int fr = lane >> 2, c0 = 2 * (lane & 3), c1 = c0 + 1;
+    if (fr < 6) {
+        const int base = fr * 6 - (fr * (fr - 1)) / 2 - fr;
+        if (c0 >= fr && c0 < 6) { rec56[base + c0] = cw0; rec56[28 + base + c0] = cr0; }
+        if (c1 >= fr && c1 < 6) { rec56[base + c1] = cw1; rec56[28 + base + c1] = cr1; }
+        if (c0 == 6) { rec56[21 + fr] = cw0; rec56[28 + 21 + fr] = cr0; }
+    } else if (fr == 6 && c0 == 6) { rec56[27] = cost_half; rec56[55] = 0.5 * cr0; }
 }
-
-// CTA-level finish: lanes' (acc, raw) of every warp -> partial[0..55]; fixed warp order.  s_red: [warps][56]
-__device__ __forceinline__ void block_neq_finish(double *s_red, double acc, double raw, double *partial) {
+// CTA-level finish of the tensor-pipe form: per-warp records summed in warp order -> partial[0..55].  s_red: [warps][56]
+__device__ __forceinline__ void block_neq_finish_mma(double *s_red, double cr0, double cr1, double cw0, double cw1, double cost_half_lane, double *partial) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    neq_store(s_red + wid * 56, lane, acc, raw, false);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost_half_lane += __shfl_xor_sync(FULL, cost_half_lane, o);
+    for (int i = lane; i < 56; i += 32) s_red[wid * 56 + i] = 0.0;
+    __syncwarp();
+    neq_mma_store(s_red + wid * 56, lane, cr0, cr1, cw0, cw1, cost_half_lane);
     __syncthreads();
     if (threadIdx.x < 56) {
         double s = 0.0;

@@ -36,15 +36,6 @@
 #ifndef VELO_RG_MANT_BITS
 #define VELO_RG_MANT_BITS 6         /* measured 4/5/6 bits: 24.4 / 23.6 / 23.2 ms per 200 pairs x 6 passes */
 #endif
-// record of `sorted`: {x, y, z, index in ring}; with ICP_MIN_F64 {x, y, index, z}, so that the candidate key (index | d2 << 32) forms in
-// the aligned register pair the 16-byte load delivered
-#ifdef ICP_MIN_F64
-#define SORTED_IDX(c) ((c).z)
-#define SORTED_Z(c) ((c).w)
-#else
-#define SORTED_IDX(c) ((c).w)
-#define SORTED_Z(c) ((c).z)
-#endif
 #define VELO_IDX_BITS 20            /* index-in-ring bits of the neighbour key */
 #define VELO_RING_BITS 12
 

@@ -75,18 +75,6 @@ __device__ __forceinline__ Window make_window(float d2b, float az, float D, floa
     return w;
 }
 
-// minimum of two candidate keys.  A key is (bits of a non-negative float) << 32 | index, i.e. the bit pattern of a non-negative
-// double, and non-negative doubles (subnormals included) order like their bit patterns: with ICP_MIN_F64 the comparison is one
-// DSETP on the FP64 pipe instead of two ISETP on the ALU pipe, which the candidate loop saturates first (rt 2 cycles per warp
-// instruction on either pipe, B300_MICROARCH.md "Pipe rates").  A NaN distance (non-finite input) never wins either way.
-__device__ __forceinline__ u64 key_min(u64 a, u64 b) {
-#ifdef ICP_MIN_F64
-    const double da = __longlong_as_double((long long)a), db = __longlong_as_double((long long)b);
-    return (u64)__double_as_longlong(da <= db ? da : db);
-#else
-    return min(a, b);
-#endif
-}
 // nearest candidate of one ring inside sorted[start, end): smallest d2, ties -> lower index in ring.  The running best is the
 // pair (bits of d2, index) compared as one unsigned 64-bit number (d2 >= 0, so its bits order like its value): branch-free,
 // whereas a "rare" improvement branch diverges in almost every iteration once 32 lanes share the loop.
@@ -98,8 +86,8 @@ __device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, in
     for (int p = start; p < end; p++) {
         const float4 c = __ldg(sorted + p);
         const float d2 = d2f_xy2(c, mxy, mz);
-        const u64 k = ((u64)__float_as_uint(d2) << 32) | (u64)(unsigned)__float_as_int(SORTED_IDX(c));
-        best = key_min(best, k);
+        const u64 k = ((u64)__float_as_uint(d2) << 32) | (u64)(unsigned)__float_as_int(c.w);
+        best = min(best, k);
     }
 }
 __device__ __forceinline__ u64 scan_init(float thr_excl) { return (u64)__float_as_uint(thr_excl) << 32; }
@@ -140,10 +128,6 @@ __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 
         if (sec == sb) break;
     }
     return m;
-}
-
-__device__ __forceinline__ u64 warp_or64(u64 v) {
-    return ((u64)__reduce_or_sync(FULL, (unsigned)(v >> 32)) << 32) | (u64)__reduce_or_sync(FULL, (unsigned)v);
 }
 
 // grid = (ctas per unit, n_units).  A unit is one frame pair with up to VELO_MAX_PASSES supplied poses (the ICP passes of
@@ -278,7 +262,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
                     if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
                 }
-#ifdef ICP_LEGACY
                 // Phase 1 (probe), only while two rings do not yet hold a candidate: rings in order of increasing elevation
                 // gap (levels of doubling tolerance, read from the ring masks), only the query's own azimuth bin of each.
 #ifdef EXP_NO_PROBE
@@ -362,93 +345,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     }
                 }
             }
-#else
-            }
-            // The search is RING-SYNCHRONOUS: the 32 queries of a chunk are consecutive points of one source ring, so they want
-            // nearly the same target rings.  Every lane computes its own ring mask and azimuth window, the warp walks the OR of
-            // the masks with warp-uniform control flow, and a lane scans ring s only if s is in its own mask (a lane that sits
-            // out has proven that ring s holds nothing within its bound, exactly as in a per-lane walk).  `cell_start` reads of a
-            // round fall into one or two cache lines and the distance loop starts converged.
-            //
-            // Phase 1 (probe), only for lanes without two rings yet (first pass / lost seeds): rings in order of increasing
-            // elevation gap (levels of doubling tolerance, read from the ring masks), only the query's own azimuth bin of each.
-#ifndef EXP_NO_PROBE
-            if (__any_sync(FULL, active && kj == KEY_INF)) {
-                const float gam_thr = make_window(thr_f, az, D, rho).gam;   // elevation tolerance of the threshold itself
-                Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq; ws.gam = 0.f;
-                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                bool live = active;
-                for (float lev = 0.0065f;; lev *= 2.0f) {
-                    live = live && kj == KEY_INF;
-                    if (!__any_sync(FULL, live)) break;
-                    ws.gam = fminf(lev, gam_thr);
-#pragma unroll
-                    for (int word = 0; word < 4; word++) {
-                        if (word >= W) break;
-                        u64 m = 0ull;
-                        if (live) { m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, ws, mask_query(el, ws.gam, rho, 0.f), false) & ~V[word]; V[word] |= m; }
-                        for (u64 M = warp_or64(m); M; M &= M - 1) {
-                            const int sb = __ffsll((long long)M) - 1, s = word * 64 + sb;
-                            const bool mine = ((m >> sb) & 1ull) && kj == KEY_INF;
-                            if (!__any_sync(FULL, mine)) continue;
-                            int p0 = 0, e0 = 0;
-                            if (mine) { const int *cs = csS + s * (VELO_AZ_BINS + 1) + bq; p0 = __ldg(cs); e0 = __ldg(cs + 1); }
-                            u64 best = scan_init(thr_excl);
-                            scan_range(sorted, p0, e0, mx, my, mz, best, st_seed);
-                            if (mine && scan_found(best, thr_excl)) merge_key(scan_key(best, s), ki, kj);
-                        }
-                    }
-                    if (!(lev < gam_thr)) live = false;
-                }
-            }
-#endif
-            // Phase 2 (exhaustive): every ring that can hold a point within the lane's current bound on d2_j (velo.h:825-848) is
-            // scanned by the lane exactly once, nearest elevation first (levels of doubling tolerance; a single level when the
-            // bound is already tight); the bound, the azimuth window and the elevation tolerance shrink whenever the runner-up
-            // improves.  A min over keys is order independent, so the walk order does not change a bit of the result.
-            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
-            Window w = make_window(bound, az, D, rho);
-#ifndef EXP_NO_PHASE2
-            {
-                u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                bool fin = !active;
-                const bool tight = w.gam <= 0.03f;      // seeded / well-probed query: one mask level, window kept for the whole pass
-                for (float lev = 0.0065f;; lev *= 2.0f) {
-                    const float gcur = tight ? w.gam : fminf(lev, w.gam);
-#pragma unroll
-                    for (int word = 0; word < 4; word++) {
-                        if (word >= W) break;
-                        u64 m = 0ull;
-                        if (!fin) { m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, w, mask_query(el, gcur, rho, sqrtf(bound)), true) & ~V[word]; V[word] |= m; }
-                        for (u64 M = warp_or64(m); M; M &= M - 1) {
-                            const int sb = __ffsll((long long)M) - 1, s = word * 64 + sb;
-                            const bool mine = (m >> sb) & 1ull;
-                            int p0 = 0, e0 = 0, p1 = 0, e1 = 0;
-                            if (mine) {
-                                const int *cs = csS + s * (VELO_AZ_BINS + 1);
-                                st_mask++;
-                                if (!w.wrapped) { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + w.b1 + 1); }
-                                else { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + w.b1 + 1); }
-                            }
-                            u64 best = scan_init(thr_excl);
-                            scan_range(sorted, p0, e0, mx, my, mz, best, st_exh);
-                            scan_range(sorted, p1, e1, mx, my, mz, best, st_exh);
-                            if (mine) {
-                                st_rings++;
-                                if (scan_found(best, thr_excl)) {
-                                    const u64 oj = kj;
-                                    merge_key(scan_key(best, s), ki, kj);
-                                    if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
-                                }
-                            }
-                        }
-                    }
-                    if (!(gcur < w.gam)) fin = true;        // every ring within the lane's tolerance was visited
-                    if (__all_sync(FULL, fin)) break;
-                }
-            }
-#endif
-#endif
             if (active) {
                 pki = ki; pkj = kj;
 

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
         float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
         int b = az_bin(atan2f(vy, vx));
         int pos = s_hist[b] + atomicAdd(&s_cur[b], 1);
-        SORTED_Z(p) = p.z; SORTED_IDX(p) = __int_as_float(i);     // (z first: with ICP_MIN_F64 the index takes its place)
+        p.w = __int_as_float(i);
         sorted[pos] = p;
     }
 }
@@ -332,32 +332,63 @@ __device__ __forceinline__ bool width_ok(float dx, const DevCalib &cal) {   // h
     return fabsf(dx) < cal.assoc_thr;
 }
 
-// The ring loop, binary search and bilinear patch of velo.h:390-492, step for step (H4/H5), one thread per keypoint.
+// The ring loop, bracket search and bilinear patch of velo.h:390-492 (H4/H5), one thread per keypoint.
 // One CTA per (camera, slot) serves every keypoint set of that image: the projections of all rings (x,y pairs, ~140 KB for a
-// KITTI frame) are first staged in shared memory, because the binary searches are scattered 8-byte reads that would otherwise
-// cost one L1 wavefront per lane.  A projection that does not fit (more than ASSOC_CAP points in the FOV) is searched in
-// global memory through the same code path.
+// KITTI frame) are first staged in shared memory, because the searches are scattered 8-byte reads.
+//  * Which rings a keypoint has to search is read from a table: for each of ASSOC_YB buckets of the image height, the bit mask of
+//    the rings that can take part in a hit for a keypoint with y in that bucket.  A hit on the ring pair (s-1, s) needs
+//    (proj[s][mid].y > kp.y) != (proj[s-1][last].y > kp.y) (velo.h:414-415): impossible when both rings lie entirely above
+//    (y > kp.y everywhere) or entirely not-above.  A ring whose two pairs are both impossible cannot influence the result, so it is
+//    not searched and `last` is -1 after it, exactly as after a ring without a bracket (the mask is a conservative superset:
+//    evaluated at both bucket edges; searching a ring that was not needed is what the reference does anyway).
+//  * The reference's binary search (velo.h:404-412) finds an index mid with proj[mid].x <= kp.x < proj[mid+1].x.  On a ring whose
+//    projected x never decreases (every ring, unless the occlusion stack pushed a z-tie, velo.h:360-366) that index is unique —
+//    the last point with x <= kp.x — so ANY search finds the reference's bracket.  Such rings get a 128-bucket x table while they
+//    are staged (start index of each bucket: points in lower buckets are strictly left of the keypoint, points in higher ones
+//    strictly right, because the bucket function is monotone) and the search is two table reads plus a scan of the keypoint's own
+//    bucket (~2 points) instead of 9 dependent steps.  A ring with a decreasing x (H4), a NaN keypoint, or a projection that does
+//    not fit in shared memory takes the reference's exact sequence of mid points.
+#ifndef ASSOC_THREADS
 #define ASSOC_THREADS 512
-#define ASSOC_CAP 24576           /* float2 entries of dynamic shared memory (192 KB) */
-#define ASSOC_YB 256              /* keypoint-y buckets of the needed-ring range table */
+#endif
+#define ASSOC_DYN_BYTES (200 * 1024)   /* dynamic shared memory: staged (x,y) pairs + the x tables */
+#define ASSOC_YB 256                   /* keypoint-y buckets of the needed-ring table */
+#define ASSOC_NB 128                   /* x buckets per ring */
+__device__ __forceinline__ int assoc_xbucket(float x, float xmin, float xscale) {   // monotone non-decreasing in x (NaN -> 0)
+    const int b = (int)((x - xmin) * xscale);
+    return min(max(b, 0), ASSOC_NB - 1);
+}
 __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, DevCalib cal, int slot0, int set0, int nsets, int cam0) {
     extern __shared__ float2 s_proj[];
     __shared__ int s_off[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_rs[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_cnt[VELO_MAX_RINGS_HARD];
     __shared__ float2 s_yr[VELO_MAX_RINGS_HARD];
+    __shared__ int s_mono[VELO_MAX_RINGS_HARD];
+    __shared__ unsigned long long s_need[ASSOC_YB + 1][VELO_MAX_RINGS_HARD / 64];   // [ASSOC_YB]: every searchable ring (keypoints outside the image)
+    __shared__ int s_w[33];
     const int cam = cam0 + blockIdx.x, slot = slot0 + blockIdx.y;
-    const int nr = B.n_rings[slot];
+    const int nr = B.n_rings[slot], NW = (nr + 63) >> 6;
     const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
     const int *pc = B.proj_count + ((size_t)slot * B.C + cam) * B.R;
     const float2 *yr = B.proj_yrange + ((size_t)slot * B.C + cam) * B.R;
     const float2 *proj = B.proj + ((size_t)slot * B.C + cam) * B.N;
     const float4 *valid = B.valid + ((size_t)slot * B.C + cam) * B.N;
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) { s_rs[i] = rs[i]; s_cnt[i] = pc[i]; s_yr[i] = yr[i]; }
+    int total = 0;
+    for (int i0 = 0; i0 < nr; i0 += blockDim.x) {                 // ring offsets in the staged array (exclusive scan of the counts)
+        const int i = i0 + threadIdx.x;
+        const int c = i < nr ? pc[i] : 0;
+        if (i < nr) { s_rs[i] = rs[i]; s_cnt[i] = c; s_yr[i] = yr[i]; s_mono[i] = 1; }
+        int t;
+        const int ex = block_excl_scan(c, s_w, t);
+        if (i < nr) s_off[i] = total + ex;
+        total += t;
+    }
+    if (threadIdx.x == 0) s_off[nr] = total;
     __syncthreads();
-    if (threadIdx.x == 0) { int o = 0; for (int s = 0; s < nr; s++) { s_off[s] = o; o += s_cnt[s]; } s_off[nr] = o; }
-    __syncthreads();
-    const bool fits = s_off[nr] <= ASSOC_CAP;
+    unsigned short *s_lut = reinterpret_cast<unsigned short *>(s_proj + total);
+    const bool fits = (size_t)total * sizeof(float2) + (size_t)nr * (ASSOC_NB + 1) * sizeof(unsigned short) <= ASSOC_DYN_BYTES;
+    const float xmin = cal.fov[cam][0], xscale = ASSOC_NB / (cal.fov[cam][1] - cal.fov[cam][0]);
     if (fits) {
         // 8-byte cp.async per projection: no register round trip, so the copies of all rings are in flight together
         for (int s = 0; s < nr; s++) {
@@ -368,103 +399,102 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // x tables: lut[s][b] = first index of ring s whose bucket is >= b (points are bucket-sorted on a ring with non-decreasing x);
+        // a decreasing x marks the ring for the exact search
+        for (int s = 0; s < nr; s++) {
+            const float2 *ps = s_proj + s_off[s];
+            unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
+            const int cnt = s_cnt[s];
+            for (int i = threadIdx.x; i <= cnt; i += blockDim.x) {
+                const float xp = i > 0 ? ps[i - 1].x : 0.f, xi = i < cnt ? ps[i].x : 0.f;
+                const int bp = i > 0 ? assoc_xbucket(xp, xmin, xscale) : -1, bi = i < cnt ? assoc_xbucket(xi, xmin, xscale) : ASSOC_NB;
+                if (i > 0 && i < cnt && xp > xi) s_mono[s] = 0;
+                for (int b = bp + 1; b <= bi; b++) lut[b] = (unsigned short)i;
+            }
+        }
+    }
+    // needed-ring masks per keypoint-y bucket
+    const float ymin = cal.fov[cam][2], ymax = cal.fov[cam][3], yscale = ASSOC_YB / (ymax - ymin);
+    for (int bkt = threadIdx.x; bkt <= ASSOC_YB; bkt += blockDim.x) {
+        const float y0 = ymin + bkt / yscale - 1e-4f, y1 = ymin + (bkt + 1) / yscale + 1e-4f;   // bucket edges, padded
+#pragma unroll
+        for (int w = 0; w < VELO_MAX_RINGS_HARD / 64; w++) {
+            unsigned long long m = 0ull;
+            for (int s2 = 64 * w; s2 < min(nr, 64 * w + 64); s2++) {
+                // pair (a,b) impossible for all y in the bucket if (ymin_a > y1 && ymin_b > y1) || (ymax_a <= y0 && ymax_b <= y0)
+                auto imp = [&](int a2, int b2) -> bool {
+                    if (a2 < 0 || b2 >= nr) return true;
+                    return (s_yr[a2].x > y1 && s_yr[b2].x > y1) || (s_yr[a2].y <= y0 && s_yr[b2].y <= y0);
+                };
+                const bool need = bkt == ASSOC_YB || !(imp(s2 - 1, s2) && imp(s2, s2 + 1));
+                if (need && s_cnt[s2] > 1) m |= 1ull << (s2 & 63);                               // rings with <= 1 points: velo.h:400-403
+            }
+            s_need[bkt][w] = m;
+        }
     }
     __syncthreads();
     const float2 *base = fits ? s_proj : proj;
     const int *off = fits ? s_off : s_rs;
-    // A hit on the ring pair (s-1, s) needs (proj[s][mid].y > kp.y) != (proj[s-1][last].y > kp.y) (velo.h:414-415): impossible
-    // when both rings lie entirely above (y > kp.y everywhere) or entirely not-above.  A ring whose two pairs are both
-    // impossible cannot influence the result, so its binary search is skipped (its `last` is never consulted); skipping a ring
-    // leaves last = -1 exactly as a ring without a bracket would.  s_first/s_last bound the rings that can be needed for a
-    // keypoint whose y falls in one of ASSOC_YB buckets of the image height (conservative: evaluated at both bucket edges).
-    __shared__ unsigned char s_first[ASSOC_YB], s_lastr[ASSOC_YB];
-    const float ymin = cal.fov[cam][2], ymax = cal.fov[cam][3], yscale = ASSOC_YB / (ymax - ymin);
-    for (int bkt = threadIdx.x; bkt < ASSOC_YB; bkt += blockDim.x) {
-        const float y0 = ymin + bkt / yscale - 1e-4f, y1 = ymin + (bkt + 1) / yscale + 1e-4f;   // bucket edges, padded
-        int f = nr, l = -1;
-        for (int s2 = 0; s2 < nr; s2++) {
-            // ring s2 is "surely not needed" for every y in [y0,y1] iff both its pairs are impossible for all such y.
-            // pair (a,b) impossible for all y in the bucket if (ymin_a > y1 && ymin_b > y1) || (ymax_a <= y0 && ymax_b <= y0).
-            auto imp = [&](int a2, int b2) -> bool {
-                if (a2 < 0 || b2 >= nr) return true;
-                return (s_yr[a2].x > y1 && s_yr[b2].x > y1) || (s_yr[a2].y <= y0 && s_yr[b2].y <= y0);
-            };
-            if (!(imp(s2 - 1, s2) && imp(s2, s2 + 1))) { if (s2 < f) f = s2; l = s2; }
-        }
-        s_first[bkt] = (unsigned char)min(f, 255); s_lastr[bkt] = (unsigned char)(l < 0 ? 0 : min(l, 255));
-        if (l < 0) { s_first[bkt] = 1; s_lastr[bkt] = 0; }     // empty range
-    }
-    __syncthreads();
     for (int si = 0; si < nsets; si++) {
         const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + (set0 + si)) * B.C + cam;
         const int F = B.n_kp[sc];
-        for (int k0 = 0; k0 < F; k0 += blockDim.x) {
-            const int k = k0 + threadIdx.x;
-            const bool act = k < F;
-            const float2 kp = act ? B.kp[sc * B.F + k] : make_float2(0.f, 0.f);
-            int last = -1, hit = 0;
-            int h_s = 0, h_mid = 0, h_last = 0;          // the bracket of the hit; its interpolation (global gathers) runs after the rounds
-            int s = nr, s_end = -1;
-            if (act) {
-                if (kp.y >= ymin && kp.y < ymax) { const int bkt = min(max((int)((kp.y - ymin) * yscale), 0), ASSOC_YB - 1); s = s_first[bkt]; s_end = s_lastr[bkt]; }
-                else { s = 0; s_end = nr - 1; }                                      // keypoint outside the image: no shortcut
-                if (nr > 255) { s = 0; s_end = nr - 1; }
-            }
-            // warp-synchronous rounds: every lane advances (cheaply) to its next needed ring, then all lanes search together
-            for (;;) {
-                while (s <= s_end) {
-                    const bool ab_p = s > 0 ? (s_yr[s - 1].x > kp.y) : true, be_p = s > 0 ? (s_yr[s - 1].y <= kp.y) : true;
-                    const bool ab_c = s_yr[s].x > kp.y, be_c = s_yr[s].y <= kp.y;
-                    const bool ab_n = (s + 1 < nr) ? (s_yr[s + 1].x > kp.y) : true, be_n = (s + 1 < nr) ? (s_yr[s + 1].y <= kp.y) : true;
-                    const bool pair_prev = !((ab_p && ab_c) || (be_p && be_c)), pair_next = !((ab_c && ab_n) || (be_c && be_n));
-                    if ((pair_prev || pair_next) && s_cnt[s] > 1) break;               // ring s needs its binary search
-                    last = -1; s++;                                                    // skipped ring / velo.h:400-403
-                }
-                const bool work = s <= s_end;
-                if (!__any_sync(FULL, work)) break;
-                if (work) {
+        for (int k = threadIdx.x; k < F; k += blockDim.x) {
+            const float2 kp = B.kp[sc * B.F + k];
+            const int bkt = (kp.y >= ymin && kp.y < ymax) ? min(max((int)((kp.y - ymin) * yscale), 0), ASSOC_YB - 1) : ASSOC_YB;
+            const bool kx_ok = kp.x == kp.x;
+            const int xb = assoc_xbucket(kp.x, xmin, xscale);
+            int last = -1, prev_s = -2, hit = 0;
+            int h_s = 0, h_mid = 0, h_last = 0;          // the bracket of the hit; its interpolation (global gathers) runs after the search
+            float2 pa = make_float2(0.f, 0.f), pb = pa;  // bracket of the previous ring
+            for (int w = 0; w < NW && !hit; w++) {
+                for (unsigned long long m = s_need[bkt][w]; m && !hit; m &= m - 1) {
+                    const int s = (w << 6) + __ffsll((long long)m) - 1;
+                    if (s != prev_s + 1) last = -1;                                  // a ring that was not searched lies in between
+                    prev_s = s;
                     const int cnt = s_cnt[s];
                     const float2 *ps = base + off[s];
-                    int lo = 0, hi = cnt - 2, mid = 0;
+                    int mid = 0;
                     bool found = false;
                     float2 a = make_float2(0.f, 0.f), b = a;
-                    // velo.h:404-412 with the same sequence of mid points, written without early `continue`s: both neighbours are
-                    // read every step and lo / hi move by selects, so the 32 lanes of a round run one instruction stream
-                    while (lo <= hi && !found) {
-                        mid = (lo + hi) >> 1;
-                        a = ps[mid]; b = ps[mid + 1];
-                        const bool left = a.x > kp.x, right = !left && (b.x <= kp.x);
-                        hi = left ? mid - 1 : hi; lo = right ? mid + 1 : lo;
-                        found = !left && !right;
+                    if (fits && s_mono[s] && kx_ok) {
+                        const unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
+                        int j = lut[xb];
+                        const int j1 = lut[xb + 1];
+                        while (j < j1 && ps[j].x <= kp.x) j++;                      // the keypoint's own bucket, ~2 points
+                        mid = j - 1;
+                        found = mid >= 0 && mid <= cnt - 2;
+                        if (found) { a = ps[mid]; b = ps[mid + 1]; }
+                    } else {
+                        // velo.h:404-412 with the same sequence of mid points
+                        int lo = 0, hi = cnt - 2;
+                        while (lo <= hi && !found) {
+                            mid = (lo + hi) >> 1;
+                            a = ps[mid]; b = ps[mid + 1];
+                            const bool left = a.x > kp.x, right = !left && (b.x <= kp.x);
+                            hi = left ? mid - 1 : hi; lo = right ? mid + 1 : lo;
+                            found = !left && !right;
+                        }
                     }
                     if (found) {
-                        if (last != -1) {
-                            const float2 *pq = base + off[s - 1];
-                            const float2 c = pq[last], d = pq[last + 1];
-                            if (((a.y > kp.y) != (c.y > kp.y)) && width_ok(__fsub_rn(a.x, b.x), cal) && width_ok(__fsub_rn(c.x, d.x), cal)) {
-                                hit = 1; h_s = s; h_mid = mid; h_last = last;
-                            }
+                        if (last != -1 && ((a.y > kp.y) != (pa.y > kp.y)) && width_ok(__fsub_rn(a.x, b.x), cal) && width_ok(__fsub_rn(pa.x, pb.x), cal)) {
+                            hit = 1; h_s = s; h_mid = mid; h_last = last;            // velo.h:413-422
                         }
-                        last = mid;                                              // velo.h:483
-                    }
-                    if (!found) last = -1;                                       // velo.h:487-489
-                    s = hit ? nr + 1 : s + 1;                                    // velo.h:490
-                    if (hit) s_end = -1;
+                        last = mid; pa = a; pb = b;                                  // velo.h:483
+                    } else last = -1;                                                // velo.h:487-489
                 }
             }
-            if (act) {
-                B.hit_tmp[sc * B.F + k] = hit;
-                if (hit) {
-                    const float2 *ps = base + off[h_s], *pq = base + off[h_s - 1];
-                    const float2 a = ps[h_mid], b = ps[h_mid + 1], c = pq[h_last], d = pq[h_last + 1];
-                    const float4 *vs = valid + s_rs[h_s], *vq = valid + s_rs[h_s - 1];
-                    const float3 i1 = lerp3(vs[h_mid], vs[h_mid + 1], a.x, b.x, kp.x);       // velo.h:445-450
-                    const float3 i2 = lerp3(vq[h_last], vq[h_last + 1], c.x, d.x, kp.x);     // velo.h:451-456
-                    const float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                        // velo.h:457-462
-                    const float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                        // velo.h:463-468
-                    const float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
-                    B.kpwd_tmp[sc * B.F + k] = make_float4(r.x, r.y, r.z, 1.0f);
-                }
+            B.hit_tmp[sc * B.F + k] = hit;
+            if (hit) {
+                const float2 *ps = base + off[h_s], *pq = base + off[h_s - 1];
+                const float2 a = ps[h_mid], b = ps[h_mid + 1], c = pq[h_last], d = pq[h_last + 1];
+                const float4 *vs = valid + s_rs[h_s], *vq = valid + s_rs[h_s - 1];
+                const float3 i1 = lerp3(vs[h_mid], vs[h_mid + 1], a.x, b.x, kp.x);       // velo.h:445-450
+                const float3 i2 = lerp3(vq[h_last], vq[h_last + 1], c.x, d.x, kp.x);     // velo.h:451-456
+                const float i1y = lerp1(a.y, b.y, a.x, b.x, kp.x);                        // velo.h:457-462
+                const float i2y = lerp1(c.y, d.y, c.x, d.x, kp.x);                        // velo.h:463-468
+                const float3 r = lerp3(make_float4(i1.x, i1.y, i1.z, 0.f), make_float4(i2.x, i2.y, i2.z, 0.f), i1y, i2y, kp.y); // velo.h:470-475
+                B.kpwd_tmp[sc * B.F + k] = make_float4(r.x, r.y, r.z, 1.0f);
             }
         }
     }
@@ -517,8 +547,8 @@ void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal,
 }
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams) {
     dim3 g(ncams, count);
-    cudaFuncSetAttribute(k_assoc_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ASSOC_CAP * sizeof(float2)));
-    PRE(VK_ASSOC_SEARCH); k_assoc_search<<<g, ASSOC_THREADS, ASSOC_CAP * sizeof(float2), L.stream>>>(B, cal, slot0, set0, nsets, cam0); POST(VK_ASSOC_SEARCH);
+    cudaFuncSetAttribute(k_assoc_search, cudaFuncAttributeMaxDynamicSharedMemorySize, ASSOC_DYN_BYTES);
+    PRE(VK_ASSOC_SEARCH); k_assoc_search<<<g, ASSOC_THREADS, ASSOC_DYN_BYTES, L.stream>>>(B, cal, slot0, set0, nsets, cam0); POST(VK_ASSOC_SEARCH);
     dim3 g2(ncams, count * nsets);
     PRE(VK_ASSOC_COMPACT); k_assoc_compact<<<g2, 256, 0, L.stream>>>(B, slot0, set0, nsets, cam0); POST(VK_ASSOC_COMPACT);
 }

@@ -20,45 +20,45 @@ __global__ void __launch_bounds__(256) k_icp_eval_fixed(DevBuffers B, const velo
     __shared__ double s_rows[8][NEQ_STAGE];
     __shared__ double s_red[8 * 56];
     __shared__ int s_cnt;
+    __shared__ RotPack s_rp;
+    __shared__ double s_pose[6];
     if (done && *done) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_cnt = 0;
+    if (tid < 6) s_pose[tid] = pose[tid];
+    __syncthreads();
+    if (tid < 3) rotpack_column(s_pose, false, tid, &s_rp);          // rotation + derivative of the trial pose, once per CTA
     __syncthreads();
     const int *rs = B.ring_start + (size_t)src_slot * (B.R + 1);
     const float4 *pts = B.pts + (size_t)src_slot * B.N;
-    DJ x[6];
-    for (int i = 0; i < 6; i++) { x[i] = dj(pose[i]); x[i].v[i] = 1.0; }
-    double acc = 0.0, raw = 0.0;
+    double cr0 = 0.0, cr1 = 0.0, cw0 = 0.0, cw1 = 0.0, cost_half = 0.0;
     int nk = 0;
     const int cap = min(B.N, max(0, (int)*n_records));      // the records the correspondence pass wrote (its query count)
     const int per = (((cap + gridDim.x - 1) / gridDim.x) + 31) & ~31;
     const int q0 = blockIdx.x * per, q1 = min(cap, q0 + per);
-    for (int qb = q0; qb < q1; qb += blockDim.x) {
+    for (int qb = q0; qb < q1; qb += blockDim.x) {              // warp-uniform trip count
         const int q = qb + tid;
         bool kept = false;
-        double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
+        double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0;
         if (q < q1) {
             const velo_icp_corr c = corr[q];
             if (c.kept == 1) {
                 // (src_ring, src_idx) were written by k_icp_pass for this source slot: in range by construction
                 const float4 p = pts[rs[c.src_ring] + c.src_idx];
                 const double k[9] = { p.x, p.y, p.z, c.normal[0], c.normal[1], c.normal[2], c.v0[0], c.v0[1], c.v0[2] };
-                DJ r[1];
-                f3dpd(k, x, r);
-                res = r[0].a;
-                for (int i = 0; i < 6; i++) J[i] = r[0].v[i];
+                lin3dpd(k, s_rp, s_pose + 3, &res, J);
                 const double bb = loss_a * loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;   // Scaled(Cauchy), velo.h:885-891
                 rho1 = weight * fmax(2.2250738585072014e-308, inv);
-                rho0h = 0.5 * weight * bb * log(sum);
+                cost_half += 0.5 * weight * bb * log(sum);
                 kept = true; nk++;
             }
         }
-        warp_accum(s_rows[wid], J, res, rho1, rho0h, kept, lane, acc, raw);
+        if (__any_sync(FULL, kept)) neq_mma_rows(s_rows[wid], lane, J, res, rho1, kept, cr0, cr1, cw0, cw1);
     }
     for (int o = 16; o > 0; o >>= 1) nk += __shfl_down_sync(FULL, nk, o);
     if (lane == 0 && nk) atomicAdd(&s_cnt, nk);
     double *pout = partial + (size_t)blockIdx.x * 64;
-    block_neq_finish(s_red, acc, raw, pout);
+    block_neq_finish_mma(s_red, cr0, cr1, cw0, cw1, cost_half, pout);
     if (tid == 0) { pout[56] = (double)s_cnt; pout[57] = (double)s_cnt; pout[58] = 0.0; }
 }
 

@@ -176,6 +176,13 @@ int  velo_gpu_projection_upload(velo_gpu_ctx *ctx, int slot, int cam, const int 
 int  velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int set, const float *kp, int F,
                           int *has_depth, float *kpwd, int *n_hits);
 
+/* install externally held association results for (slot, cam, set) — the keypoints / has_depth / keypoints_with_depth containers of
+ * velo.h:601-606 as the caller holds them (kp = F x (x,y), has_depth[F] = -1 or an index < n_hits, kpwd = n_hits x {x,y,z,*}) —
+ * so that velo_gpu_visual_residuals / velo_gpu_frame_to_frame can read them from device memory.  Used by the frameToFrame
+ * adapter of velo_dropin.hpp, which receives these containers from main.cpp:388-405. */
+int  velo_gpu_assoc_upload(velo_gpu_ctx *ctx, int slot, int cam, int set, const float *kp, int F,
+                           const int *has_depth, const float *kpwd, int n_hits);
+
 /* ICP block of frameToFrame (velo.h:800-895) at a supplied pose: transform_point (utility.h:97-103),
  * per-ring 1-NN + top-2 rings + third point + normal (velo.h:806-874), cost3DPD residual/Jacobian
  * (costfunctions.h:17-58) and the normal equations Ceres would form (velo.h:885-902).
@@ -224,6 +231,22 @@ typedef struct velo_f2f_report {
 int  velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, int slot_S, int set2,
                              const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
                              int enable_icp, int icp_skip, double transform[6], velo_f2f_report *report);
+
+/* The same schedule for every frame pair (slot s, slot s-1) of a batch at once, s in [slot0 + (first_has_prev ? 0 : 1), slot0 + count):
+ * the batch's ingest / index / projection / association stages must have run (velo_gpu_batch_run); frame1 = slot s with its tracked
+ * keypoints (set 1), frame2 = slot s-1 with its detected keypoints (set 0), matches as uploaded with the batch, icp_skip from the
+ * context's params, no landmarks.  All pairs solve side by side on the device (one Levenberg-Marquardt controller per pair);
+ * this is the live, pose-dependent loop of velo.h:616-907 — each correspondence pass runs at the pose its pair has reached.
+ * transforms [count][6] in/out (entry of a slot without a previous scan is left untouched), reports [count] nullable. */
+int  velo_gpu_batch_frame_to_frame(velo_gpu_ctx *ctx, int slot0, int count, int first_has_prev, int enable_visual, int enable_icp,
+                                   double *transforms, velo_f2f_report *reports);
+
+/* residual types of the LAST f2f iteration of the preceding velo_gpu_frame_to_frame call, per camera and match: sel[cam *
+ * max_matches + i] is a bit mask, 1 = 3D3D, 2 = 2D2D, 4 = 3D2D, 8 = 2D3D (blocks are added in that order, velo.h:662-789).  This is
+ * what frameToFrame leaves in good_matches / residual_type (velo.h:624-625,690-692).  capacity >= num_cams * max_matches. */
+int  velo_gpu_f2f_selection(velo_gpu_ctx *ctx, unsigned char *sel, int capacity);
+/* util::pose_mat2vec (utility.h:67-82; despite its name: 6-vector -> 4x4): T = [R(angle-axis) | t], row-major 4x4. */
+int  velo_pose_vec2mat(const double transform[6], double T[16]);
 
 /* triangulatePoint (velo.h:1027-1130) for n_landmarks at once: each landmark is a 3-parameter problem
  * over its 3-D observations (triangulation3D, TrivialLoss) and 2-D observations (triangulation2D, Scaled(Cauchy)), listed in

@@ -421,42 +421,97 @@ def test_cuda_path_against_golden_fixture(velo, oracle):
         c.close()
 
 
-def test_cpp_dropin_header(velo, oracle, calib, params, tmp_path):
-    """include/velo_dropin.hpp (the reference's C++ signatures) compiled with g++ against libvelo_gpu.so and driven like
-    main.cpp drives the reference; outputs compared with the oracle."""
+def test_cpp_dropin_header(velo, oracle, calib, tmp_path):
+    """include/velo_dropin.hpp (the reference's C++ signatures) compiled with g++ against libvelo_gpu.so and driven like main.cpp
+    drives the reference, on a KITTI-layout tree written here (<root>/00/calib.txt, <root>/00/velodyne/%06d.bin; kitti.h:59-152):
+    loadCalibration -> ScansLRU::get -> ScanData(dataset, frame) -> projectLidarToCamera -> featureDepthAssociation ->
+    icpCorrespondences -> frameToFrame(velo.h:598-614 parameter list), then LRU eviction / slot reuse and recycled host addresses.
+    Every output is compared with the oracle."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pkg = os.path.join(root, "vision-enhanced-lidar-odometry_b200")
     exe = tmp_path / "dropin_main"
-    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "dropin_main.cpp"),
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "dropin_main.cpp"),
                     "-L", pkg, "-lvelo_gpu", f"-Wl,-rpath,{pkg}", "-o", str(exe)], check=True)
     P, Tr, w, h = velo.synth.calib_raw(0)
-    np.concatenate([P, Tr, np.array([w, h], np.float32)]).astype(np.float32).tofile(tmp_path / "calib.bin")
-    raw0, raw1 = small_scan(velo, 7, range(10, 50), 2), small_scan(velo, 8, range(10, 50), 2)
-    raw0.tofile(tmp_path / "scan0.bin"); raw1.tofile(tmp_path / "scan1.bin")
-    kp = velo.synth.features(8, 1500)[0][0]
-    kp.tofile(tmp_path / "kp.bin")
-    pose = velo.synth.pose_guess(8, 0)
+    seq = tmp_path / "00"
+    (seq / "velodyne").mkdir(parents=True)
+    with open(seq / "calib.txt", "w") as f:                                    # the layout kitti.h:66-105 parses
+        for c in range(4):
+            f.write(f"P{c}: " + " ".join("%.9g" % v for v in P[12 * c: 12 * c + 12]) + "\n")
+        f.write("Tr: " + " ".join("%.9g" % v for v in Tr) + "\n")
+    FR0, F, ncam = 100, 1200, 2
+    raws = [small_scan(velo, FR0 + k, range(8, 56), 2) for k in range(5)]
+    for k, raw in enumerate(raws):
+        raw.tofile(seq / "velodyne" / ("%06d.bin" % k))
+    kpA0 = velo.synth.features(FR0, F)[0]
+    _, kpB1, m1 = velo.synth.features(FR0 + 1, F)
+    kpA0.tofile(tmp_path / "kpA0.bin"); kpB1.tofile(tmp_path / "kpB1.bin")
+    prm = velo.api.default_params(max_slots=6, icp_skip=4, max_features=1500, max_matches=1500)     # what dropin_main.cpp sets
+    MM, Fp = prm.max_matches, prm.max_features
+    matches = np.zeros((ncam, MM, 2), np.int32); nm = np.zeros(ncam, np.int32)
+    for cam in range(ncam):
+        idx = np.nonzero(m1[cam])[0]
+        nm[cam] = len(idx); matches[cam, : len(idx), 0] = idx; matches[cam, : len(idx), 1] = idx
+    np.concatenate([matches.ravel(), nm]).astype(np.int32).tofile(tmp_path / "matches.bin")
+    pose = velo.synth.pose_guess(FR0 + 1, 0)
     pose.tofile(tmp_path / "pose.bin")
-    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(tmp_path), "00", str(w), str(h)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    pts1, rs1, _ = oracle.segment(raw1, calib)
-    pts0, rs0, _ = oracle.segment(raw0, calib)
-    for cam in (0, 1):
-        rc, proj, valid = oracle.project(pts1, rs1, calib, cam)
-        assert np.array_equal(np.fromfile(tmp_path / f"out_rc{cam}.bin", np.int32), rc)
-        assert np.fromfile(tmp_path / f"out_proj{cam}.bin", np.float32).tobytes() == proj.tobytes()
-        hd, kw = oracle.depth_assoc(valid, proj, rc, kp)
-        assert np.array_equal(np.fromfile(tmp_path / f"out_hd{cam}.bin", np.int32), hd)
-        assert np.fromfile(tmp_path / f"out_kpwd{cam}.bin", np.float32).tobytes() == kw.tobytes()
-        assert (hd >= 0).sum() > 100
+    seg = [oracle.segment(raw, calib)[:2] for raw in raws]
+    pts0, rs0 = seg[0]; pts1, rs1 = seg[1]
+    hd = {}; kw = {}
+    for fr, kp_all in ((0, kpA0), (1, kpB1)):
+        hd[fr] = np.full((ncam, Fp), 0, np.int32); kw[fr] = np.zeros((ncam, Fp, 4), np.float32)
+        for cam in range(ncam):
+            rc, proj, valid = oracle.project(*seg[fr], calib, cam)
+            h_, k_ = oracle.depth_assoc(valid, proj, rc, kp_all[cam])
+            hd[fr][cam, :F] = h_; kw[fr][cam, : len(k_)] = k_
+            if fr == 1:
+                assert np.array_equal(np.fromfile(tmp_path / f"out_rc{cam}.bin", np.int32), rc)
+                assert np.fromfile(tmp_path / f"out_proj{cam}.bin", np.float32).tobytes() == proj.tobytes()
+                assert np.array_equal(np.fromfile(tmp_path / f"out_hd{cam}.bin", np.int32), h_)
+                assert np.fromfile(tmp_path / f"out_kpwd{cam}.bin", np.float32).tobytes() == k_.tobytes()
+                assert (h_ >= 0).sum() > 100
     corr = np.fromfile(tmp_path / "out_corr.bin", velo.abi.ICP_CORR_DTYPE)
-    ocorr, oneq, okept = oracle.icp_pass(pts1, rs1, pts0, rs0, pose, 1, 5, params, 1)
+    ocorr, oneq, okept = oracle.icp_pass(pts1, rs1, pts0, rs0, pose, 1, 5, prm, 1)
     for f in ("src_ring", "src_idx", "kept", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
         assert np.array_equal(corr[f], ocorr[f]), f
     neq = np.fromfile(tmp_path / "out_neq.bin", np.float64)
     np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max())
+    # ---- frameToFrame adapter vs the oracle's frame_to_frame
+    pad = lambda a: np.concatenate([a, np.zeros((a.shape[0], Fp - a.shape[1]) + a.shape[2:], a.dtype)], 1)
+    vis = (pad(kpB1), pad(kpA0), hd[1], hd[0], kw[1], kw[0], nm, matches)
+    guess = np.array([0, 0, 0, 0, 0, 1.0])
+    ox, orep = oracle.frame_to_frame(pts1, rs1, pts0, rs0, calib, prm, guess, vis, 1, prm.icp_skip)
+    gx = np.fromfile(tmp_path / "out_f2f_transform.bin", np.float64)
+    rep = velo.abi.F2FReport.from_buffer_copy((tmp_path / "out_f2f_report.bin").read_bytes())
+    assert rep.n_solves == orep["n_solves"] == prm.f2f_iterations * prm.icp_iterations
+    assert list(rep.n_blocks)[: rep.n_solves] == orep["n_blocks"] and list(rep.lm_iterations)[: rep.n_solves] == orep["lm_iterations"]
+    np.testing.assert_allclose(gx, ox, rtol=0, atol=1e-8)
+    truth = velo.synth.pose(FR0 + 1)
+    assert np.abs(gx[:3] - truth[:3]).max() < 2e-3 and np.abs(gx[3:] - truth[3:]).max() < 2e-2
+    T = np.fromfile(tmp_path / "out_f2f_T.bin", np.float64).reshape(4, 4)
+    from scipy.spatial.transform import Rotation
+    np.testing.assert_allclose(T[:3, :3], Rotation.from_rotvec(gx[:3]).as_matrix(), atol=1e-14)
+    np.testing.assert_allclose(T[:3, 3], gx[3:], atol=0); assert np.array_equal(T[3], [0, 0, 0, 1])
+    # good_matches / residual_type = the block list of the LAST f2f iteration, assembled at the pose the first iteration ended with
+    ob, _ = oracle.visual(vis[0], vis[1], vis[2], vis[3], vis[4], vis[5], nm, matches, calib, prm, orep["pose"][prm.icp_iterations - 1], prm.f2f_iterations)
+    for cam in range(ncam):
+        gm = np.fromfile(tmp_path / f"out_f2f_good{cam}.bin", np.int32).reshape(-1, 3)
+        ex = ob[ob["cam"] == cam]
+        assert len(gm) == len(ex) > 200
+        assert np.array_equal(gm[:, 0], matches[cam, ex["match"], 0]) and np.array_equal(gm[:, 1], matches[cam, ex["match"], 1])
+        assert np.array_equal(gm[:, 2], ex["type"])                              # RESIDUAL_* (velo.h:3-8) numbering == VELO_RES_*
+    assert np.isfinite(np.fromfile(tmp_path / "out_f2f_lm_transform.bin", np.float64)).all()
+    # ---- ScansLRU eviction / slot reuse, recycled host addresses
+    rc, proj, _ = oracle.project(*seg[0], calib, 0)
+    assert np.array_equal(np.fromfile(tmp_path / "out_rc_lru0.bin", np.int32), rc) and np.fromfile(tmp_path / "out_proj_lru0.bin", np.float32).tobytes() == proj.tobytes()
+    for k in (4, 2):
+        rc, proj, _ = oracle.project(*seg[k], calib, 1)
+        assert np.array_equal(np.fromfile(tmp_path / f"out_rc_foreign{k}.bin", np.int32), rc), k
+        assert np.fromfile(tmp_path / f"out_proj_foreign{k}.bin", np.float32).tobytes() == proj.tobytes(), k
 
 
 def test_random_ragged_ring_clouds(velo, oracle, calib, params, ctx):
@@ -780,5 +835,58 @@ def test_xyz_scan_records_equal_kitti_records(velo, calib):
             outs.append((icp.tobytes(), vis.tobytes(), hd.tobytes(), nh.tobytes(), pts.tobytes(), rs.tobytes()))
             assert icp[1:, :, 56].min() > 1000 and vis[1:, :, 56].min() > 100
         assert outs[0] == outs[1]
+    finally:
+        c.close()
+
+
+def test_batched_frame_to_frame_vs_oracle(velo, oracle, calib):
+    """velo_gpu_batch_frame_to_frame: the live frameToFrame loop (velo.h:616-907: every correspondence pass at the pose its pair has
+    reached) for all frame pairs of a batch side by side, one LM controller per pair.  Each pair vs the oracle's frame_to_frame from
+    the reference's start (0,0,0,0,0,1): same LM path (blocks, iterations, accepted steps, termination reasons), poses to 1e-8; and
+    vs the single-pair entry point."""
+    F = 800
+    prm = velo.api.default_params(max_slots=4, max_features=F, max_matches=F, icp_skip=4, max_rings=64)
+    c = velo.api.Context(prm, calib)
+    try:
+        b = velo.synth.Batch(60, 4, prm)
+        c.batch_upload(0, b)
+        A = velo.abi
+        c.batch_run(0, 4, A.STAGE_INGEST | A.STAGE_INDEX | A.STAGE_PROJECT | A.STAGE_ASSOC)
+        guess = np.array([0, 0, 0, 0, 0, 1.0])
+        t, reps = c.batch_frame_to_frame(0, 4, np.tile(guess, (4, 1)))
+        assert np.array_equal(t[0], guess) and reps[0]["n_solves"] == 0           # the halo slot has no previous scan
+        seg = [oracle.segment(b.scans[s, : b.n_points[s]], calib)[:2] for s in range(4)]
+        hd = np.zeros((4, 2, 2, F), np.int32); kw = np.zeros((4, 2, 2, F, 4), np.float32)
+        for s in range(4):
+            for cam in (0, 1):
+                rc, proj, valid = oracle.project(*seg[s], calib, cam)
+                for st in (0, 1):
+                    h, k = oracle.depth_assoc(valid, proj, rc, b.kp[s, st, cam])
+                    hd[s, st, cam] = h; kw[s, st, cam, : len(k)] = k
+        for s in (1, 2, 3):
+            vis = (b.kp[s, 1], b.kp[s - 1, 0], hd[s, 1], hd[s - 1, 0], kw[s, 1], kw[s - 1, 0], b.n_matches[s], b.matches[s])
+            ox, orep = oracle.frame_to_frame(*seg[s], *seg[s - 1], calib, prm, guess, vis, 1, prm.icp_skip)
+            g = reps[s]
+            assert g["n_solves"] == orep["n_solves"] == 6
+            assert g["n_blocks"] == orep["n_blocks"] and g["reason"] == orep["reason"], (s, g["n_blocks"], orep["n_blocks"])
+            assert g["lm_iterations"] == orep["lm_iterations"] and g["accepted_steps"] == orep["accepted_steps"]
+            np.testing.assert_allclose(g["pose"], orep["pose"], rtol=0, atol=1e-8)
+            np.testing.assert_allclose(t[s], ox, rtol=0, atol=1e-8)
+            truth = velo.synth.pose(60 + s)
+            assert np.abs(t[s][:3] - truth[:3]).max() < 1e-3 and np.abs(t[s][3:] - truth[3:]).max() < 2e-2
+            cat = np.concatenate([b.matches[s, cam, : b.n_matches[s, cam]] for cam in (0, 1)])
+            sx, srep = c.frame_to_frame(s, 1, s - 1, 0, guess, n_matches=b.n_matches[s], matches=cat, enable_icp=1, icp_skip=prm.icp_skip)
+            assert srep["lm_iterations"] == g["lm_iterations"] and srep["n_blocks"] == g["n_blocks"]
+            np.testing.assert_allclose(sx, t[s], rtol=0, atol=1e-9)
+        # ICP terms only / visual terms only
+        t2, reps2 = c.batch_frame_to_frame(0, 4, np.tile(guess, (4, 1)), enable_visual=0)
+        ox, orep = oracle.frame_to_frame(*seg[2], *seg[1], calib, prm, guess, None, 1, prm.icp_skip)
+        assert reps2[2]["n_blocks"] == orep["n_blocks"] and reps2[2]["lm_iterations"] == orep["lm_iterations"]
+        np.testing.assert_allclose(t2[2], ox, rtol=0, atol=1e-8)
+        t3, reps3 = c.batch_frame_to_frame(0, 4, np.tile(guess, (4, 1)), enable_icp=0)
+        vis = (b.kp[2, 1], b.kp[1, 0], hd[2, 1], hd[1, 0], kw[2, 1], kw[1, 0], b.n_matches[2], b.matches[2])
+        ox, orep = oracle.frame_to_frame(*seg[2], *seg[1], calib, prm, guess, vis, 0, prm.icp_skip)
+        assert reps3[2]["n_solves"] == orep["n_solves"] == prm.f2f_iterations and reps3[2]["n_blocks"] == orep["n_blocks"]
+        np.testing.assert_allclose(t3[2], ox, rtol=0, atol=1e-7)
     finally:
         c.close()

@@ -36,6 +36,23 @@ for skip in (1, 20, 200):
                       "lm_iterations": rep["lm_iterations"], "blocks_first_solve": rep["n_blocks"][0],
                       "pose_err_vs_truth": [float(np.abs(gx[:3] - truth[:3]).max()), float(np.abs(gx[3:] - truth[3:]).max())],
                       "max_abs_diff_vs_oracle": float(np.abs(gx - ox).max())}))
+# ---- f1 batched: the live frameToFrame loop for B frame pairs side by side (one LM controller per pair), full scans, icp_skip = 1
+Bn = int(os.environ.get("F2F_BATCH", "200"))
+prm_b = api.default_params(max_slots=Bn + 1, max_points=131072, max_rings=64, max_features=2000, max_matches=2000, icp_skip=1)
+cb = api.Context(prm_b, cal)
+bb = synth.Batch(2000, Bn + 1, prm_b)
+cb.batch_upload(0, bb)
+A = velo.abi
+cb.batch_run(0, Bn + 1, A.STAGE_INGEST | A.STAGE_INDEX | A.STAGE_PROJECT | A.STAGE_ASSOC)
+g0 = np.tile(guess, (Bn + 1, 1))
+for name, kw in (("ICP + visual terms", {}), ("ICP terms only", {"enable_visual": 0}), ("visual terms only (the shipped configuration, main.cpp:43)", {"enable_icp": 0})):
+    g = best(lambda: cb.batch_frame_to_frame(0, Bn + 1, g0, **kw), 2)
+    tb, rb = cb.batch_frame_to_frame(0, Bn + 1, g0, **kw)
+    err = np.array([[np.abs(tb[s][:3] - synth.pose(2000 + s)[:3]).max(), np.abs(tb[s][3:] - synth.pose(2000 + s)[3:]).max()] for s in range(1, Bn + 1)])
+    print(json.dumps({"row": "f1 batched frame_to_frame, " + name, "pairs": Bn, "icp_skip": 1, "gpu_ms": round(g * 1e3, 1), "pairs_per_s": round(Bn / g, 1),
+                      "lm_iterations_mean_per_solve": [round(float(np.mean([r["lm_iterations"][k] for r in rb[1:]])), 2) for k in range(rb[1]["n_solves"])],
+                      "pose_err_vs_truth_median": [float(np.median(err[:, 0])), float(np.median(err[:, 1]))], "pose_err_vs_truth_max": [float(err[:, 0].max()), float(err[:, 1].max())]}))
+cb.close()
 # ---- f4: matchFeatures, 3000 x 3000 FREAK-sized descriptors
 rng = np.random.default_rng(0)
 q = _descriptors(rng, 3000); t_ = np.concatenate([_descriptors(rng, 2000, q[:2000], flips=14), _descriptors(rng, 1000)])

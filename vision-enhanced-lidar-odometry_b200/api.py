@@ -55,10 +55,14 @@ def lib():
     L.velo_gpu_project.argtypes = [_P, C.c_int, C.c_int]
     L.velo_gpu_project_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]
     L.velo_gpu_depth_assoc.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]
+    L.velo_gpu_assoc_upload.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int]
+    L.velo_gpu_f2f_selection.argtypes = [_P, _P, C.c_int]
+    L.velo_pose_vec2mat.argtypes = [_P, _P]
     L.velo_gpu_icp_pass.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]
     L.velo_gpu_icp_passes.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
     L.velo_gpu_visual_residuals.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]
     L.velo_gpu_frame_to_frame.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]
+    L.velo_gpu_batch_frame_to_frame.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]
     L.velo_gpu_match_hamming.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, C.POINTER(C.c_int), _P, _P]
     L.velo_gpu_triangulate.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]
     L.velo_gpu_batch_upload.argtypes = [_P, C.c_int, C.c_int, _P]
@@ -139,6 +143,14 @@ def kitti_format_pose(T):
     if rc:
         raise VeloError(rc, "format_pose")
     return buf.value.decode()
+
+
+def pose_vec2mat(transform):
+    """util::pose_mat2vec (utility.h:67-82): 6-vector -> 4x4"""
+    t = np.ascontiguousarray(transform, np.float64)
+    T = np.zeros(16, np.float64)
+    lib().velo_pose_vec2mat(_ptr(t), _ptr(T))
+    return T.reshape(4, 4)
 
 
 class PinnedPool:
@@ -267,6 +279,16 @@ class Context:
         self._ck(self.L.velo_gpu_depth_assoc(self.h, slot, cam, set_, _ptr(kp), F, _ptr(hd), _ptr(kpwd), C.byref(nh)))
         return hd[:F], kpwd[:nh.value]
 
+    def assoc_upload(self, slot, cam, set_, kp, has_depth, kpwd):
+        kp = np.ascontiguousarray(kp, np.float32).reshape(-1, 2); hd = np.ascontiguousarray(has_depth, np.int32)
+        kw = np.ascontiguousarray(kpwd, np.float32).reshape(-1, 4)
+        self._ck(self.L.velo_gpu_assoc_upload(self.h, slot, cam, set_, _ptr(kp), len(kp), _ptr(hd), _ptr(kw) if len(kw) else None, len(kw)))
+
+    def f2f_selection(self):
+        sel = np.zeros(self.prm.num_cams * self.prm.max_matches, np.uint8)
+        self._ck(self.L.velo_gpu_f2f_selection(self.h, _ptr(sel), len(sel)))
+        return sel.reshape(self.prm.num_cams, self.prm.max_matches)
+
     def icp_pass(self, slot_M, slot_S, pose, it, skip, want_corr=True):
         pose = np.ascontiguousarray(pose, np.float64)
         cap = self.prm.max_points
@@ -358,6 +380,19 @@ class Context:
         bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
                              _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis, batch.scans.shape[-1])
         self._ck(self.L.velo_gpu_batch_frontend(self.h, slot0, batch.count, C.addressof(bi), chunk, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
+
+    def batch_frame_to_frame(self, slot0, count, transforms, enable_visual=1, enable_icp=1, first_has_prev=0):
+        """velo.h:616-907 for every frame pair of the batch at once; transforms [count][6] -> (transforms, [report dict per slot])"""
+        t = np.ascontiguousarray(transforms, np.float64).reshape(count, 6).copy()
+        reps = (abi.F2FReport * count)()
+        self._ck(self.L.velo_gpu_batch_frame_to_frame(self.h, slot0, count, first_has_prev, enable_visual, enable_icp, _ptr(t), C.addressof(reps)))
+        out = []
+        for rep in reps:
+            n = rep.n_solves
+            out.append({"n_solves": n, "lm_iterations": list(rep.lm_iterations)[:n], "accepted_steps": list(rep.accepted_steps)[:n], "reason": list(rep.reason)[:n],
+                        "n_blocks": list(rep.n_blocks)[:n], "initial_cost": list(rep.initial_cost)[:n], "final_cost": list(rep.final_cost)[:n],
+                        "pose": np.array([list(rep.pose[i]) for i in range(n)])})
+        return t, out
 
     def batch_counts(self, slot0, count):
         npnt = np.zeros(count, np.int32); nr = np.zeros(count, np.int32)

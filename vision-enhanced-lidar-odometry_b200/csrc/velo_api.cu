@@ -37,11 +37,20 @@ struct velo_gpu_ctx {
     velo_icp_corr *d_corr = nullptr;
     VisMatchOut *d_mout = nullptr;
     int *d_lm_valid = nullptr; float4 *d_lm_xyz = nullptr;
-    // device-resident solve
-    LmState *d_lm = nullptr; double *d_pose = nullptr, *d_eval_partial = nullptr, *d_eval_out = nullptr, *d_zero_neq = nullptr;
-    unsigned char *d_sel = nullptr;
+    // device-resident solve of up to f2f_cap frame pairs at once (buffers grown on demand, velo_gpu_frame_to_frame needs 1)
+    int f2f_cap = 0, f2f_last_n = 0;
+    LmState *d_f2f_lm = nullptr, *h_f2f_lm = nullptr;
+    IcpUnit *d_f2f_icp_units = nullptr, *h_f2f_icp_units = nullptr;
+    VisUnit *d_f2f_vis_units = nullptr, *h_f2f_vis_units = nullptr;
+    IcpFrozen *d_f2f_frozen = nullptr;
+    unsigned char *d_f2f_sel = nullptr;
+    double *d_f2f_poses = nullptr, *d_f2f_icp_partial = nullptr, *d_f2f_icp_out = nullptr, *d_f2f_eval_partial = nullptr, *d_f2f_eval_out = nullptr,
+           *d_f2f_vis_partial = nullptr, *d_f2f_vis_out = nullptr;
+    int *d_f2f_ndone = nullptr;
     // Hamming matcher scratch (grown on demand)
-    unsigned long long *d_hq = nullptr, *d_ht = nullptr; int *d_hidx = nullptr, *d_hdist = nullptr; size_t ham_cap_q = 0, ham_cap_t = 0;
+    unsigned long long *d_hq = nullptr, *d_ht = nullptr, *d_hbest = nullptr; size_t ham_cap_q = 0, ham_cap_t = 0;
+    // triangulation scratch (one arena, grown on demand)
+    char *d_tri = nullptr; size_t tri_cap = 0;
     std::vector<int> h_npoints;     // host copy of n_points per slot (single-frame path)
     std::vector<int> h_stride;      // staging of raw_stride (must outlive the asynchronous copy)
     // timing
@@ -310,8 +319,6 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     CKC(dalloc(ctx, &ctx->d_vis_partial, vpart * 64)); CKC(dalloc(ctx, &ctx->d_vis_out, n_vis_units * VELO_NEQ_STRIDE));
     CKC(dalloc(ctx, &ctx->d_corr, N * P)); CKC(dalloc(ctx, &ctx->d_mout, C * MM)); CKC(dalloc(ctx, &ctx->d_flags, 4));
     CKC(dalloc(ctx, &ctx->d_lm_valid, C * MM)); CKC(dalloc(ctx, &ctx->d_lm_xyz, C * MM));
-    CKC(dalloc(ctx, &ctx->d_lm, 1)); CKC(dalloc(ctx, &ctx->d_pose, 8)); CKC(dalloc(ctx, &ctx->d_eval_partial, (size_t)296 * 64));
-    CKC(dalloc(ctx, &ctx->d_eval_out, VELO_NEQ_STRIDE)); CKC(dalloc(ctx, &ctx->d_zero_neq, VELO_NEQ_STRIDE)); CKC(dalloc(ctx, &ctx->d_sel, C * MM));
     ctx->h_npoints.assign(S, 0); ctx->h_stride.assign(S, 4);
     // calibration for the device
     DevCalib &d = ctx->dcal; memset(&d, 0, sizeof(d));
@@ -328,13 +335,28 @@ extern "C" int velo_gpu_create(int device, const velo_gpu_params *prm, const vel
     return VELO_OK;
 }
 
+static void f2f_free(velo_gpu_ctx *ctx) {
+    void *dev[] = { ctx->d_f2f_lm, ctx->d_f2f_icp_units, ctx->d_f2f_vis_units, ctx->d_f2f_frozen, ctx->d_f2f_sel, ctx->d_f2f_poses, ctx->d_f2f_icp_partial,
+                    ctx->d_f2f_icp_out, ctx->d_f2f_eval_partial, ctx->d_f2f_eval_out, ctx->d_f2f_vis_partial, ctx->d_f2f_vis_out, ctx->d_f2f_ndone };
+    for (void *p : dev) if (p) cudaFree(p);
+    if (ctx->h_f2f_lm) cudaFreeHost(ctx->h_f2f_lm);
+    if (ctx->h_f2f_icp_units) cudaFreeHost(ctx->h_f2f_icp_units);
+    if (ctx->h_f2f_vis_units) cudaFreeHost(ctx->h_f2f_vis_units);
+    ctx->d_f2f_lm = nullptr; ctx->h_f2f_lm = nullptr; ctx->d_f2f_icp_units = nullptr; ctx->h_f2f_icp_units = nullptr; ctx->d_f2f_vis_units = nullptr;
+    ctx->h_f2f_vis_units = nullptr; ctx->d_f2f_frozen = nullptr; ctx->d_f2f_sel = nullptr; ctx->d_f2f_poses = nullptr; ctx->d_f2f_icp_partial = nullptr;
+    ctx->d_f2f_icp_out = nullptr; ctx->d_f2f_eval_partial = nullptr; ctx->d_f2f_eval_out = nullptr; ctx->d_f2f_vis_partial = nullptr; ctx->d_f2f_vis_out = nullptr;
+    ctx->d_f2f_ndone = nullptr; ctx->f2f_cap = 0;
+}
+
 extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
     if (!ctx) return VELO_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
-    if (ctx->d_hq) { cudaFree(ctx->d_hq); cudaFree(ctx->d_hidx); cudaFree(ctx->d_hdist); }
+    if (ctx->d_hq) { cudaFree(ctx->d_hq); cudaFree(ctx->d_hbest); }
     if (ctx->d_ht) cudaFree(ctx->d_ht);
+    if (ctx->d_tri) cudaFree(ctx->d_tri);
+    f2f_free(ctx);
     if (ctx->h_icp_units) cudaFreeHost(ctx->h_icp_units);
     if (ctx->h_vis_units) cudaFreeHost(ctx->h_vis_units);
     for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -552,6 +574,27 @@ extern "C" int velo_gpu_depth_assoc(velo_gpu_ctx *ctx, int slot, int cam, int se
     return VELO_OK;
 }
 
+extern "C" int velo_gpu_assoc_upload(velo_gpu_ctx *ctx, int slot, int cam, int set, const float *kp, int F, const int *has_depth, const float *kpwd, int n_hits) {
+    if (!ctx) return VELO_ERR_INVALID_ARG;
+    if (check_slot(ctx, slot) || check_cam(ctx, cam)) return VELO_ERR_INVALID_ARG;
+    if (set < 0 || set >= VELO_NUM_KP_SETS || F < 0 || n_hits < 0 || n_hits > F || (F > 0 && (!kp || !has_depth)) || (n_hits > 0 && !kpwd))
+        return fail(ctx, VELO_ERR_INVALID_ARG, "bad association arrays");
+    if (F > ctx->B.F) return fail(ctx, VELO_ERR_CAPACITY, "more keypoints than max_features");
+    for (int i = 0; i < F; i++) if (has_depth[i] < -1 || has_depth[i] >= n_hits) return fail(ctx, VELO_ERR_INVALID_ARG, "has_depth entry outside keypoints_with_depth");
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + set) * B.C + cam;
+    if (F > 0) {
+        CK(cudaMemcpyAsync(B.kp + sc * B.F, kp, (size_t)F * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B.has_depth + sc * B.F, has_depth, (size_t)F * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n_hits > 0) CK(cudaMemcpyAsync(B.kpwd + sc * B.F, kpwd, (size_t)n_hits * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.n_kp + sc, &F, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.n_hits + sc, &n_hits, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // F / n_hits are stack variables; the caller's arrays may go away
+    return VELO_OK;
+}
+
 static void init_icp_unit(const velo_gpu_ctx *ctx, IcpUnit *u, int src, int tgt, int skip) {
     memset(u, 0, sizeof(*u));
     u->src_slot = src; u->tgt_slot = tgt; u->skip = skip; u->n_pass = 0;
@@ -671,7 +714,7 @@ extern "C" int velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1,
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     const int ctas = 32;
     launch_visual(launcher(ctx), B, ctx->dcal, sc_d_vis(ctx), 1, vis_tun(ctx), lm_valid ? ctx->d_lm_valid : nullptr, lm_valid ? ctx->d_lm_xyz : nullptr,
-                  sc_vis_partial(ctx), sc_vis_out(ctx), ctx->d_mout, ctas, VisFixed{ nullptr, nullptr, nullptr, nullptr }, ctx->d_flags);
+                  sc_vis_partial(ctx), sc_vis_out(ctx), ctx->d_mout, ctas, VisFixed{ nullptr, nullptr, nullptr, 0, 0 }, ctx->d_flags);
     CK(cudaGetLastError());
     double out[VELO_NEQ_STRIDE];
     int bad = 0;
@@ -694,14 +737,125 @@ extern "C" int velo_gpu_visual_residuals(velo_gpu_ctx *ctx, int slot1, int set1,
 }
 
 // ------------------------------------------------------------------------------------------------ device-resident frameToFrame (f1)
+static int check_range(velo_gpu_ctx *ctx, int slot0, int count);
+#define F2F_EVAL_CTAS_MAX 148
+#define F2F_VIS_CTAS_MAX 32
+struct F2FJob { int slot_M, set1, slot_S, set2; };
+
+// buffers for n simultaneous solves (kept; grown when a larger batch arrives)
+static int f2f_ensure(velo_gpu_ctx *ctx, int n) {
+    if (n <= ctx->f2f_cap) return VELO_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    f2f_free(ctx);
+    const DevBuffers &B = ctx->B;
+    const size_t N = B.N, CM = (size_t)B.C * B.MM, runs = (size_t)launch_icp_runs_cap(B.N);
+#define F2F_ALLOC(ptr, count) do { CK(cudaMalloc((void **)&(ptr), (count) * sizeof(*(ptr)))); CK(cudaMemsetAsync((ptr), 0, (count) * sizeof(*(ptr)), ctx->stream)); } while (0)
+    F2F_ALLOC(ctx->d_f2f_lm, (size_t)n); F2F_ALLOC(ctx->d_f2f_icp_units, (size_t)n); F2F_ALLOC(ctx->d_f2f_vis_units, (size_t)n);
+    F2F_ALLOC(ctx->d_f2f_frozen, (size_t)n * N); F2F_ALLOC(ctx->d_f2f_sel, (size_t)n * CM); F2F_ALLOC(ctx->d_f2f_poses, (size_t)n * 6);
+    F2F_ALLOC(ctx->d_f2f_icp_partial, (size_t)n * runs * VELO_MAX_PASSES * 64); F2F_ALLOC(ctx->d_f2f_icp_out, (size_t)n * VELO_NEQ_STRIDE);
+    F2F_ALLOC(ctx->d_f2f_eval_partial, (size_t)n * F2F_EVAL_CTAS_MAX * 64); F2F_ALLOC(ctx->d_f2f_eval_out, (size_t)n * VELO_NEQ_STRIDE);
+    F2F_ALLOC(ctx->d_f2f_vis_partial, (size_t)n * F2F_VIS_CTAS_MAX * 64); F2F_ALLOC(ctx->d_f2f_vis_out, (size_t)n * VELO_NEQ_STRIDE);
+    F2F_ALLOC(ctx->d_f2f_ndone, (size_t)4);
+#undef F2F_ALLOC
+    CK(cudaMallocHost((void **)&ctx->h_f2f_lm, (size_t)n * sizeof(LmState)));
+    CK(cudaMallocHost((void **)&ctx->h_f2f_icp_units, (size_t)n * sizeof(IcpUnit)));
+    CK(cudaMallocHost((void **)&ctx->h_f2f_vis_units, (size_t)n * sizeof(VisUnit)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->f2f_cap = n;
+    return VELO_OK;
+}
+
+// frameToFrame (velo.h:616-907) for n independent frame pairs at once.  Per f2f iteration the visual block list of every pair is
+// frozen at its current pose (k_visual, free mode, type masks kept per pair); per ICP iteration the correspondences are frozen
+// (k_icp_pass writes compact records per pair); then all pairs run their Levenberg-Marquardt solves side by side: evaluation
+// kernels over (pair, CTA), one controller thread per pair, converged pairs drop out.  The host looks at a counter of finished
+// pairs every 8 controller steps, and once per solve reads the n poses back: the pose constants of the NEXT correspondence pass
+// (cos / sin / 1/theta) are formed with the host libm so that the narrowed float queries equal the reference's bit for bit (H8).
+static int f2f_run(velo_gpu_ctx *ctx, int n, const F2FJob *jobs, bool visual, const int *d_lmv, const float4 *d_lmx, int enable_icp, int icp_skip,
+                   double *transforms, velo_f2f_report *reports) {
+    const int F2F = ctx->prm.f2f_iterations, ICP = enable_icp ? ctx->prm.icp_iterations : 1;
+    if (F2F < 1 || ICP < 1 || F2F * ICP > VELO_MAX_SOLVES) return fail(ctx, VELO_ERR_CAPACITY, "f2f_iterations * icp_iterations exceeds VELO_MAX_SOLVES");
+    int rc = f2f_ensure(ctx, n); if (rc) return rc;
+    const DevBuffers &B = ctx->B;
+    Launcher L = launcher(ctx);
+    const VisTun tun = vis_tun(ctx);
+    const int max_lm = 50, CM = B.C * B.MM;
+    const int eval_ctas = std::max(1, std::min(F2F_EVAL_CTAS_MAX, (ctx->sm_count * 8 + n - 1) / n));
+    const int vis_ctas = n == 1 ? F2F_VIS_CTAS_MAX : 4;
+    const int icp_ctas = auto_ctas(ctx, n, n == 1 ? ctx->icp_partial_ctas : 32);
+    if (reports) memset(reports, 0, (size_t)n * sizeof(velo_f2f_report));
+    CK(cudaMemcpyAsync(ctx->d_f2f_poses, transforms, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_lm_init(L, ctx->d_f2f_lm, n, ctx->d_f2f_poses, max_lm, ctx->d_f2f_ndone);
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    int solve = 0;
+    for (int iter = 1; iter <= F2F; iter++) {
+        if (visual) {   // freeze the visual block list of this f2f iteration at each pair's current pose (velo.h:622-792)
+            CK(cudaStreamSynchronize(ctx->stream));     // the unit staging below is host memory an earlier copy may still read
+            for (int u = 0; u < n; u++) {
+                VisUnit *vu = &ctx->h_f2f_vis_units[u];
+                memset(vu, 0, sizeof(*vu));
+                vu->slot1 = jobs[u].slot_M; vu->set1 = jobs[u].set1; vu->slot2 = jobs[u].slot_S; vu->set2 = jobs[u].set2; vu->iter = iter;
+            }
+            CK(cudaMemcpyAsync(ctx->d_f2f_vis_units, ctx->h_f2f_vis_units, (size_t)n * sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
+            launch_visual(L, B, ctx->dcal, ctx->d_f2f_vis_units, n, tun, d_lmv, d_lmx, ctx->d_f2f_vis_partial, ctx->d_f2f_vis_out, nullptr, vis_ctas,
+                          VisFixed{ nullptr, ctx->d_f2f_sel, ctx->d_f2f_lm, CM, 1 }, ctx->d_flags);
+        }
+        for (int ii = 0; ii < ICP; ii++, solve++) {
+            if (enable_icp) {   // freeze the ICP correspondences at each pair's current pose (velo.h:806-894)
+                CK(cudaStreamSynchronize(ctx->stream));
+                for (int u = 0; u < n; u++) {
+                    IcpUnit *iu = &ctx->h_f2f_icp_units[u];
+                    init_icp_unit(ctx, iu, jobs[u].slot_M, jobs[u].slot_S, icp_skip);
+                    add_icp_pass(ctx, iu, transforms + 6 * (size_t)u, iter);
+                }
+                CK(cudaMemcpyAsync(ctx->d_f2f_icp_units, ctx->h_f2f_icp_units, (size_t)n * sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
+                launch_icp(L, B, ctx->dcal, ctx->d_f2f_icp_units, n, 1, icp_ctas, ctx->d_f2f_icp_partial, ctx->d_f2f_icp_out, 1, nullptr, 0, ctx->d_f2f_frozen, B.N);
+            }
+            launch_lm_init(L, ctx->d_f2f_lm, n, nullptr, max_lm, ctx->d_f2f_ndone);
+            int n_done = 0;
+            for (int ev = 0; ev <= max_lm && n_done < n;) {
+                for (int k = 0; k < 8 && ev <= max_lm; k++, ev++) {   // a few controller steps per host look
+                    if (visual)
+                        launch_visual(L, B, ctx->dcal, ctx->d_f2f_vis_units, n, tun, d_lmv, d_lmx, ctx->d_f2f_vis_partial, ctx->d_f2f_vis_out, nullptr, vis_ctas,
+                                      VisFixed{ ctx->d_f2f_sel, nullptr, ctx->d_f2f_lm, CM, 0 }, nullptr);
+                    if (enable_icp)
+                        launch_icp_eval(L, B, n, ctx->d_f2f_frozen, B.N, ctx->d_f2f_icp_out, ctx->d_f2f_icp_units, ctx->d_f2f_lm, ctx->prm.loss_thresh_3DPD,
+                                        ctx->prm.weight_3DPD, ctx->d_f2f_eval_partial, eval_ctas, ctx->d_f2f_eval_out);
+                    launch_lm_step(L, ctx->d_f2f_lm, n, enable_icp ? ctx->d_f2f_eval_out : nullptr, visual ? ctx->d_f2f_vis_out : nullptr, ctx->d_f2f_ndone);
+                }
+                CK(cudaMemcpyAsync(&n_done, ctx->d_f2f_ndone, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            CK(cudaMemcpyAsync(ctx->h_f2f_lm, ctx->d_f2f_lm, (size_t)n * sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaGetLastError());
+            for (int u = 0; u < n; u++) {
+                const LmState &hs = ctx->h_f2f_lm[u];
+                memcpy(transforms + 6 * (size_t)u, hs.x, 6 * sizeof(double));
+                if (reports) {
+                    velo_f2f_report &rep = reports[u];
+                    const int k = rep.n_solves++;
+                    rep.lm_iterations[k] = hs.iter; rep.accepted_steps[k] = hs.accepted; rep.reason[k] = hs.reason; rep.n_blocks[k] = hs.n_blocks;
+                    rep.initial_cost[k] = hs.init_cost; rep.final_cost[k] = hs.cost;
+                    memcpy(rep.pose[k], hs.x, 6 * sizeof(double));
+                }
+            }
+        }
+    }
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->f2f_last_n = n;
+    if (bad) return fail(ctx, VELO_ERR_INVALID_ARG, "a match index is outside the keypoint set it refers to");
+    return VELO_OK;
+}
+
 extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, int slot_S, int set2,
                                        const int *n_matches, const int *matches, const int *lm_valid, const float *lm_xyz,
                                        int enable_icp, int icp_skip, double transform[6], velo_f2f_report *report) {
     if (!ctx) return VELO_ERR_INVALID_ARG;
     if (check_slot(ctx, slot_M) || check_slot(ctx, slot_S)) return VELO_ERR_INVALID_ARG;
     if (!transform || icp_skip < 1 || set1 < 0 || set1 >= VELO_NUM_KP_SETS || set2 < 0 || set2 >= VELO_NUM_KP_SETS) return fail(ctx, VELO_ERR_INVALID_ARG, "bad argument");
-    const int F2F = ctx->prm.f2f_iterations, ICP = enable_icp ? ctx->prm.icp_iterations : 1;
-    if (F2F < 1 || ICP < 1 || F2F * ICP > VELO_MAX_SOLVES) return fail(ctx, VELO_ERR_CAPACITY, "f2f_iterations * icp_iterations exceeds VELO_MAX_SOLVES");
     CK(cudaSetDevice(ctx->device));
     int st = slot_status(ctx, slot_M); if (st) return st;
     st = slot_status(ctx, slot_S); if (st) return st;
@@ -723,57 +877,64 @@ extern "C" int velo_gpu_frame_to_frame(velo_gpu_ctx *ctx, int slot_M, int set1, 
             off += n_matches[c];
         }
         CK(cudaMemcpyAsync(B.n_matches + (size_t)slot_M * C, n_matches, C * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));     // the caller's arrays may go away
     }
-    Launcher L = launcher(ctx);
-    const VisTun tun = vis_tun(ctx);
-    const int *d_lmv = (visual && lm_valid) ? ctx->d_lm_valid : nullptr;
-    const float4 *d_lmx = (visual && lm_valid) ? ctx->d_lm_xyz : nullptr;
-    velo_f2f_report rep; memset(&rep, 0, sizeof(rep));
-    const int eval_ctas = 148, max_lm = 50;
-    for (int iter = 1; iter <= F2F; iter++) {
-        VisUnit *vu = sc_h_vis(ctx);
-        if (visual) {   // freeze the visual block list of this f2f iteration at the current transform (velo.h:622-792)
-            memset(vu, 0, sizeof(*vu));
-            vu->slot1 = slot_M; vu->set1 = set1; vu->slot2 = slot_S; vu->set2 = set2; vu->iter = iter;
-            memcpy(vu->pose, transform, 6 * sizeof(double));
-            CK(cudaMemcpyAsync(sc_d_vis(ctx), vu, sizeof(VisUnit), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));     // the scratch unit is rewritten below
-            launch_visual(L, B, ctx->dcal, sc_d_vis(ctx), 1, tun, d_lmv, d_lmx, sc_vis_partial(ctx), sc_vis_out(ctx), nullptr, 32,
-                          VisFixed{ nullptr, ctx->d_sel, nullptr, nullptr }, ctx->d_flags);
-        }
-        for (int ii = 0; ii < ICP; ii++) {
-            if (enable_icp) {   // freeze the ICP correspondences at the current transform (velo.h:806-894)
-                init_icp_unit(ctx, sc_h_icp(ctx), slot_M, slot_S, icp_skip);
-                add_icp_pass(ctx, sc_h_icp(ctx), transform, iter);
-                CK(cudaMemcpyAsync(sc_d_icp(ctx), sc_h_icp(ctx), sizeof(IcpUnit), cudaMemcpyHostToDevice, ctx->stream));
-                launch_icp(L, B, ctx->dcal, sc_d_icp(ctx), 1, 1, auto_ctas(ctx, 1, ctx->icp_partial_ctas), sc_icp_partial(ctx), sc_icp_out(ctx), ctx->B.P, ctx->d_corr);
-            }
-            CK(cudaMemcpyAsync(ctx->d_pose, transform, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));     // `transform` / h_icp_units are host memory reused below
-            launch_lm_init(L, ctx->d_lm, ctx->d_pose, max_lm);
-            LmState hs; memset(&hs, 0, sizeof(hs));
-            for (int ev = 0; ev <= max_lm && !hs.done; ) {
-                for (int k = 0; k < 4 && ev <= max_lm; k++, ev++) {   // a few controller steps per host look
-                    if (visual)
-                        launch_visual(L, B, ctx->dcal, sc_d_vis(ctx), 1, tun, d_lmv, d_lmx, sc_vis_partial(ctx), sc_vis_out(ctx), nullptr, 32,
-                                      VisFixed{ ctx->d_sel, nullptr, ctx->d_lm->xt_ptr(), ctx->d_lm->done_ptr() });
-                    if (enable_icp)
-                        launch_icp_eval(L, B, ctx->d_corr, sc_icp_out(ctx) + 58 /* number of records the pass wrote */, slot_M, ctx->d_lm, ctx->prm.loss_thresh_3DPD,
-                                        ctx->prm.weight_3DPD, ctx->d_eval_partial, eval_ctas, ctx->d_eval_out);
-                    launch_lm_step(L, ctx->d_lm, enable_icp ? ctx->d_eval_out : ctx->d_zero_neq, visual ? sc_vis_out(ctx) : ctx->d_zero_neq);
-                }
-                CK(cudaMemcpyAsync(&hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-            }
-            CK(cudaGetLastError());
-            memcpy(transform, hs.x, 6 * sizeof(double));
-            const int k = rep.n_solves++;
-            rep.lm_iterations[k] = hs.iter; rep.accepted_steps[k] = hs.accepted; rep.reason[k] = hs.reason; rep.n_blocks[k] = hs.n_blocks;
-            rep.initial_cost[k] = hs.init_cost; rep.final_cost[k] = hs.cost;
-            memcpy(rep.pose[k], hs.x, 6 * sizeof(double));
-        }
+    const F2FJob job = { slot_M, set1, slot_S, set2 };
+    return f2f_run(ctx, 1, &job, visual, (visual && lm_valid) ? ctx->d_lm_valid : nullptr, (visual && lm_valid) ? ctx->d_lm_xyz : nullptr,
+                   enable_icp, icp_skip, transform, report);
+}
+
+// the same for the frame pairs (slot s, slot s-1) of a batch whose ingest / index / projection / association stages have run
+// (velo_gpu_batch_run): frame1 = slot s with its tracked keypoints (set 1), frame2 = slot s-1 with its detected keypoints (set 0),
+// matches as uploaded with the batch; no landmarks.
+extern "C" int velo_gpu_batch_frame_to_frame(velo_gpu_ctx *ctx, int slot0, int count, int first_has_prev, int enable_visual, int enable_icp,
+                                             double *transforms, velo_f2f_report *reports) {
+    if (!ctx || !transforms) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    if (!enable_visual && !enable_icp) return fail(ctx, VELO_ERR_INVALID_ARG, "nothing to solve: neither visual nor ICP terms");
+    CK(cudaSetDevice(ctx->device));
+    const int skip_first = (first_has_prev && slot0 > 0) ? 0 : 1;
+    const int n = count - skip_first;
+    if (n <= 0) return VELO_OK;
+    std::vector<int> stv(count);
+    CK(cudaMemcpyAsync(stv.data(), ctx->B.status + slot0, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < count; i++) if (stv[i] != 0) return fail(ctx, stv[i], "a scan of the batch has more rings than max_rings");
+    std::vector<F2FJob> jobs(n);
+    for (int u = 0; u < n; u++) { const int s = slot0 + skip_first + u; jobs[u] = F2FJob{ s, 1, s - 1, 0 }; }
+    return f2f_run(ctx, n, jobs.data(), enable_visual != 0, nullptr, nullptr, enable_icp, ctx->prm.icp_skip,
+                   transforms + 6 * (size_t)skip_first, reports ? reports + skip_first : nullptr);
+}
+
+extern "C" int velo_gpu_f2f_selection(velo_gpu_ctx *ctx, unsigned char *sel, int capacity) {
+    if (!ctx || !sel) return VELO_ERR_INVALID_ARG;
+    const size_t n = (size_t)ctx->B.C * ctx->B.MM;
+    if ((size_t)capacity < n) return fail(ctx, VELO_ERR_CAPACITY, "capacity smaller than num_cams * max_matches");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_f2f_sel || ctx->f2f_last_n != 1) return fail(ctx, VELO_ERR_STATE, "no preceding velo_gpu_frame_to_frame call");
+    CK(cudaMemcpyAsync(sel, ctx->d_f2f_sel, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VELO_OK;
+}
+
+// util::pose_mat2vec (utility.h:67-82): ceres::AngleAxisToRotationMatrix [recall: for theta^2 > DBL_EPSILON the Rodrigues form
+// R = cos I + (1 - cos) a a^T + sin [a]x with a = w / theta, else the first-order I + [w]x] + translation
+extern "C" int velo_pose_vec2mat(const double x[6], double T[16]) {
+    if (!x || !T) return VELO_ERR_INVALID_ARG;
+    double R[3][3];
+    const double th2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    if (th2 > DBL_EPSILON) {
+        const double th = sqrt(th2), wx = x[0] / th, wy = x[1] / th, wz = x[2] / th, c = cos(th), s = sin(th);
+        R[0][0] = c + wx * wx * (1.0 - c);      R[1][0] = wz * s + wx * wy * (1.0 - c); R[2][0] = -wy * s + wx * wz * (1.0 - c);
+        R[0][1] = wx * wy * (1.0 - c) - wz * s; R[1][1] = c + wy * wy * (1.0 - c);      R[2][1] = wx * s + wy * wz * (1.0 - c);
+        R[0][2] = wy * s + wx * wz * (1.0 - c); R[1][2] = -wx * s + wy * wz * (1.0 - c); R[2][2] = c + wz * wz * (1.0 - c);
+    } else {
+        R[0][0] = 1.0; R[1][0] = x[2]; R[2][0] = -x[1];
+        R[0][1] = -x[2]; R[1][1] = 1.0; R[2][1] = x[0];
+        R[0][2] = x[1]; R[1][2] = -x[0]; R[2][2] = 1.0;
     }
-    if (report) *report = rep;
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T[4 * i + j] = R[i][j]; T[4 * i + 3] = x[3 + i]; }
+    T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
     return VELO_OK;
 }
 
@@ -787,32 +948,36 @@ extern "C" int velo_gpu_triangulate(velo_gpu_ctx *ctx, int n, const int *off3, c
     const int n3 = off3[n] - off3[0], n2 = off2[n] - off2[0];
     if (off3[0] != 0 || off2[0] != 0 || (n3 > 0 && !obs3) || (n2 > 0 && !obs2) || ((n3 + n2) > 0 && !camera_poses)) return fail(ctx, VELO_ERR_INVALID_ARG, "bad observation arrays");
     CK(cudaSetDevice(ctx->device));
-    // scratch for this call (landmark batches are small next to the scans; no persistent buffers are kept)
-    int *d_off3 = nullptr, *d_off2 = nullptr, *d_has = nullptr, *d_it = nullptr; velo_tri_obs3 *d_o3 = nullptr; velo_tri_obs2 *d_o2 = nullptr;
-    double *d_poses = nullptr; float *d_init = nullptr, *d_out = nullptr;
-    int rc = VELO_OK;
-#define TRY(call) do { if (rc == VELO_OK && (call) != cudaSuccess) rc = fail(ctx, VELO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError())); } while (0)
-    TRY(cudaMalloc((void **)&d_off3, (n + 1) * sizeof(int))); TRY(cudaMalloc((void **)&d_off2, (n + 1) * sizeof(int)));
-    TRY(cudaMalloc((void **)&d_o3, (size_t)(n3 > 0 ? n3 : 1) * sizeof(velo_tri_obs3))); TRY(cudaMalloc((void **)&d_o2, (size_t)(n2 > 0 ? n2 : 1) * sizeof(velo_tri_obs2)));
-    TRY(cudaMalloc((void **)&d_poses, (size_t)(n_frames > 0 ? n_frames : 1) * 6 * sizeof(double)));
-    TRY(cudaMalloc((void **)&d_out, (size_t)n * 3 * sizeof(float))); TRY(cudaMalloc((void **)&d_it, n * sizeof(int)));
-    if (has_init) { TRY(cudaMalloc((void **)&d_has, n * sizeof(int))); TRY(cudaMalloc((void **)&d_init, (size_t)n * 3 * sizeof(float))); }
-    TRY(cudaMemcpyAsync(d_off3, off3, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    TRY(cudaMemcpyAsync(d_off2, off2, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if (n3 > 0) TRY(cudaMemcpyAsync(d_o3, obs3, (size_t)n3 * sizeof(velo_tri_obs3), cudaMemcpyHostToDevice, ctx->stream));
-    if (n2 > 0) TRY(cudaMemcpyAsync(d_o2, obs2, (size_t)n2 * sizeof(velo_tri_obs2), cudaMemcpyHostToDevice, ctx->stream));
-    if (n_frames > 0) TRY(cudaMemcpyAsync(d_poses, camera_poses, (size_t)n_frames * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (has_init) { TRY(cudaMemcpyAsync(d_has, has_init, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); TRY(cudaMemcpyAsync(d_init, init_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); }
-    if (rc == VELO_OK) {
-        launch_triangulate(launcher(ctx), n, d_off3, d_o3, d_off2, d_o2, d_poses, n_frames, ctx->dcal, ctx->prm.loss_thresh_3D2D, ctx->prm.weight_3D2D, d_init, d_has, d_out, d_it);
-        TRY(cudaGetLastError());
-        TRY(cudaMemcpyAsync(out_xyz, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        if (iterations) TRY(cudaMemcpyAsync(iterations, d_it, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        TRY(cudaStreamSynchronize(ctx->stream));
+    // scratch: one arena kept by the context and grown on demand (no allocation on the steady-state path)
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_off = up((size_t)(n + 1) * sizeof(int)), b_o3 = up((size_t)std::max(n3, 1) * sizeof(velo_tri_obs3)), b_o2 = up((size_t)std::max(n2, 1) * sizeof(velo_tri_obs2)),
+                 b_pose = up((size_t)std::max(n_frames, 1) * 6 * sizeof(double)), b_xyz = up((size_t)n * 3 * sizeof(float)), b_int = up((size_t)n * sizeof(int));
+    const size_t need = 2 * b_off + b_o3 + b_o2 + b_pose + 2 * b_xyz + 2 * b_int;
+    if (need > ctx->tri_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_tri) { cudaFree(ctx->d_tri); ctx->d_tri = nullptr; ctx->tri_cap = 0; }
+        CK(cudaMalloc((void **)&ctx->d_tri, need + need / 2));
+        ctx->tri_cap = need + need / 2;
     }
-#undef TRY
-    cudaFree(d_off3); cudaFree(d_off2); cudaFree(d_o3); cudaFree(d_o2); cudaFree(d_poses); cudaFree(d_out); cudaFree(d_it); cudaFree(d_has); cudaFree(d_init);
-    return rc;
+    char *a = ctx->d_tri;
+    int *d_off3 = (int *)a; a += b_off; int *d_off2 = (int *)a; a += b_off;
+    velo_tri_obs3 *d_o3 = (velo_tri_obs3 *)a; a += b_o3; velo_tri_obs2 *d_o2 = (velo_tri_obs2 *)a; a += b_o2;
+    double *d_poses = (double *)a; a += b_pose;
+    float *d_out = (float *)a; a += b_xyz; float *d_init = (float *)a; a += b_xyz;
+    int *d_it = (int *)a; a += b_int; int *d_has = (int *)a;
+    CK(cudaMemcpyAsync(d_off3, off3, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off2, off2, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (n3 > 0) CK(cudaMemcpyAsync(d_o3, obs3, (size_t)n3 * sizeof(velo_tri_obs3), cudaMemcpyHostToDevice, ctx->stream));
+    if (n2 > 0) CK(cudaMemcpyAsync(d_o2, obs2, (size_t)n2 * sizeof(velo_tri_obs2), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_frames > 0) CK(cudaMemcpyAsync(d_poses, camera_poses, (size_t)n_frames * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (has_init) { CK(cudaMemcpyAsync(d_has, has_init, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); CK(cudaMemcpyAsync(d_init, init_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); }
+    launch_triangulate(launcher(ctx), n, d_off3, d_o3, d_off2, d_o2, d_poses, n_frames, ctx->dcal, ctx->prm.loss_thresh_3D2D, ctx->prm.weight_3D2D,
+                       has_init ? d_init : nullptr, has_init ? d_has : nullptr, d_out, d_it);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_xyz, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (iterations) CK(cudaMemcpyAsync(iterations, d_it, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VELO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ Hamming matcher (f4)
@@ -827,19 +992,23 @@ extern "C" int velo_gpu_match_hamming(velo_gpu_ctx *ctx, const uint8_t *query, i
     const int words = desc_bytes / 8;
     const size_t qb = (size_t)n_query * desc_bytes, tb = (size_t)n_train * desc_bytes;
     if (qb > ctx->ham_cap_q) {
-        if (ctx->d_hq) { cudaFree(ctx->d_hq); cudaFree(ctx->d_hidx); cudaFree(ctx->d_hdist); }
-        CK(cudaMalloc((void **)&ctx->d_hq, qb)); CK(cudaMalloc((void **)&ctx->d_hidx, n_query * sizeof(int))); CK(cudaMalloc((void **)&ctx->d_hdist, n_query * sizeof(int)));
+        if (ctx->d_hq) { cudaFree(ctx->d_hq); cudaFree(ctx->d_hbest); ctx->d_hq = nullptr; ctx->d_hbest = nullptr; ctx->ham_cap_q = 0; }
+        CK(cudaMalloc((void **)&ctx->d_hq, qb)); CK(cudaMalloc((void **)&ctx->d_hbest, (size_t)n_query * sizeof(unsigned long long)));
         ctx->ham_cap_q = qb;
     }
     if (tb > ctx->ham_cap_t) { if (ctx->d_ht) cudaFree(ctx->d_ht); CK(cudaMalloc((void **)&ctx->d_ht, tb ? tb : 8)); ctx->ham_cap_t = tb; }
     CK(cudaMemcpyAsync(ctx->d_hq, query, qb, cudaMemcpyHostToDevice, ctx->stream));
     if (tb) CK(cudaMemcpyAsync(ctx->d_ht, train, tb, cudaMemcpyHostToDevice, ctx->stream));
-    launch_hamming(launcher(ctx), ctx->d_hq, n_query, ctx->d_ht, n_train, words, ctx->d_hidx, ctx->d_hdist);
+    launch_hamming(launcher(ctx), ctx->d_hq, n_query, ctx->d_ht, n_train, words, ctx->d_hbest, ctx->sm_count);
     CK(cudaGetLastError());
-    std::vector<int> idx(n_query), dist(n_query);
-    CK(cudaMemcpyAsync(idx.data(), ctx->d_hidx, n_query * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(dist.data(), ctx->d_hdist, n_query * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> key(n_query);
+    CK(cudaMemcpyAsync(key.data(), ctx->d_hbest, (size_t)n_query * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> idx(n_query), dist(n_query);
+    for (int i = 0; i < n_query; i++) {
+        if (key[i] == ~0ull) { idx[i] = -1; dist[i] = 0x7fffffff; }               // empty train set
+        else { idx[i] = (int)(key[i] & 0xffffffffull); dist[i] = (int)(key[i] >> 32); }
+    }
     if (best_idx) memcpy(best_idx, idx.data(), n_query * sizeof(int));
     if (best_dist) memcpy(best_dist, dist.data(), n_query * sizeof(int));
     if (n_train == 0) return VELO_OK;                      // BFMatcher returns no matches for an empty train set
@@ -968,7 +1137,7 @@ static int run_stages(velo_gpu_ctx *ctx, const Launcher &L, int slot0, int count
         if (skip_first) CK(cudaMemsetAsync(ctx->d_vis_out + (size_t)slot0 * V * VELO_NEQ_STRIDE, 0, (size_t)V * VELO_NEQ_STRIDE * sizeof(double), st));
         launch_visual(L, B, ctx->dcal, ctx->d_vis_units + (size_t)s_first * V, n_units, vis_tun(ctx), nullptr, nullptr,
                       ctx->d_vis_partial + (size_t)s_first * V * 4 * 64, ctx->d_vis_out + (size_t)s_first * V * VELO_NEQ_STRIDE, nullptr, 4,
-                      VisFixed{ nullptr, nullptr, nullptr, nullptr }, ctx->d_flags);
+                      VisFixed{ nullptr, nullptr, nullptr, 0, 0 }, ctx->d_flags);
     }
     CK(cudaGetLastError());
     return VELO_OK;

@@ -105,23 +105,25 @@ struct VisTun {
     int en2d2d, en3d2d, abs_trunc, pad;
 };
 
-// fixed-block-list mode of the visual kernel (device-resident solve): frozen type masks per (camera, match), pose read from
-// device memory, convergence flag of the solver.  All members may be null.
-struct VisFixed { const unsigned char *sel_in; unsigned char *sel_out; const double *pose; const int *done; };
-
-// per-match parity record of the visual kernel: up to 3 blocks
-struct VisMatchOut { int n; int pad; velo_vis_block b[3]; };
-
-// state of the device-resident Levenberg-Marquardt solve (velo_solve.cu); lives in device memory
+// state of the device-resident Levenberg-Marquardt solve (velo_solve.cu), one per frame pair being solved; lives in device memory
 struct LmState {
     double x[6], xt[6], delta[6];     // accepted pose, trial pose, last step
     double H[21], g[6];               // robustified normal equations at x
     double cost, init_cost, model_change, radius, decrease_factor;
     double function_tolerance, gradient_tolerance, parameter_tolerance;
     int iter, done, phase, reason, accepted, max_iterations, n_blocks, pad;
-    __host__ __device__ const double *xt_ptr() const { return xt; }
-    __host__ __device__ const int *done_ptr() const { return &done; }
 };
+
+// The visual kernel inside the device-resident solve.  Per unit u: sel_in / sel_out + u * sel_stride = frozen type masks per (camera,
+// match) (fixed mode reads sel_in and applies no gate; free mode may record what it chose in sel_out); lm[u] supplies the pose
+// (the accepted pose x when freezing the block list, else the trial pose xt) and the convergence flag.  All members may be null.
+struct VisFixed { const unsigned char *sel_in; unsigned char *sel_out; const LmState *lm; int sel_stride; int use_accepted; };
+
+// one frozen cost3DPD block of the device-resident solve: what velo.h:875-884 captured (normal, plane point, source point)
+struct __align__(16) IcpFrozen { float n[3]; int src; float o[3]; int kept; };     // src = index into pts of the source slot
+
+// per-match parity record of the visual kernel: up to 3 blocks
+struct VisMatchOut { int n; int pad; velo_vis_block b[3]; };
 
 struct Launcher {
     cudaStream_t stream;
@@ -136,19 +138,26 @@ void launch_index(const Launcher &L, const DevBuffers &B, const DevCalib &cal, i
 void launch_project(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count);
 void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, int slot0, int count, int set0, int nsets, int cam0, int ncams);
 // units: device array [n_units]; partial: [n_units][launch_icp_runs_cap(B.N)][VELO_MAX_PASSES][64] doubles; out: [n_units][out_stride_passes][VELO_NEQ_STRIDE];
-// corr optional (single unit): records of its last pass, or with corr_stride > 0 of every pass ([pass][corr_stride])
+// corr optional (single unit): records of its last pass, or with corr_stride > 0 of every pass ([pass][corr_stride]);
+// frozen optional: compact records of the LAST pass per unit, [unit][frozen_stride]
 int launch_icp_runs_cap(int max_points);
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
-                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride = 0);
+                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride = 0,
+                IcpFrozen *frozen = nullptr, int frozen_stride = 0);
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
                    const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas,
-                   VisFixed fx = VisFixed{ nullptr, nullptr, nullptr, nullptr }, int *bad_flag = nullptr);
+                   VisFixed fx = VisFixed{ nullptr, nullptr, nullptr, 0, 0 }, int *bad_flag = nullptr);
 
-void launch_lm_init(const Launcher &L, LmState *S, const double *d_pose, int max_iterations);
-void launch_icp_eval(const Launcher &L, const DevBuffers &B, const velo_icp_corr *corr, const double *n_records, int src_slot, const LmState *S,
-                     double loss_a, double weight, double *partial, int ctas, double *out);
-void launch_lm_step(const Launcher &L, LmState *S, const double *e_icp, const double *e_vis);
-void launch_hamming(const Launcher &L, const unsigned long long *q, int nq, const unsigned long long *t, int nt, int words, int *best_idx, int *best_dist);
+// device-resident solve of n frame pairs at once (unit u <-> S[u]); poses nullable (keep the accepted pose, restart the controller)
+void launch_lm_init(const Launcher &L, LmState *S, int n, const double *d_poses, int max_iterations, int *n_done);
+// frozen: [n][frozen_stride]; icp_out: [n][VELO_NEQ_STRIDE] of the correspondence pass ([58] = records written); units[u].src_slot = source scan;
+// partial: [n][ctas][64]; out: [n][VELO_NEQ_STRIDE]
+void launch_icp_eval(const Launcher &L, const DevBuffers &B, int n, const IcpFrozen *frozen, int frozen_stride, const double *icp_out, const IcpUnit *units,
+                     const LmState *S, double loss_a, double weight, double *partial, int ctas, double *out);
+// e_icp / e_vis: [n][VELO_NEQ_STRIDE] or null (term absent)
+void launch_lm_step(const Launcher &L, LmState *S, int n, const double *e_icp, const double *e_vis, int *n_done);
+// best: [nq] keys (distance << 32 | train index), all ones where the train set is empty
+void launch_hamming(const Launcher &L, const unsigned long long *q, int nq, const unsigned long long *t, int nt, int words, unsigned long long *best, int sm_count);
 void launch_triangulate(const Launcher &L, int n, const int *off3, const velo_tri_obs3 *obs3, const int *off2, const velo_tri_obs2 *obs2,
                         const double *poses, int n_frames, const DevCalib &cal, double loss_a, double weight,
                         const float *init_xyz, const int *has_init, float *out_xyz, int *iterations);

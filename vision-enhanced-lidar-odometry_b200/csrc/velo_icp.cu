@@ -148,7 +148,8 @@ __host__ __device__ inline int icp_blocks(int queries) { return (queries + ICP_B
 __host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(max_points) * ICP_WARPS; }
 
 __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
-                                                          double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride) {
+                                                          double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
+                                                          IcpFrozen *__restrict__ frozen, int frozen_stride) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
     __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
@@ -397,6 +398,12 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         kept = true;
                     }
                 }
+                if (frozen && ps == NP - 1) {      // compact record for the device-resident solve (two 16-byte stores)
+                    IcpFrozen f;
+                    f.n[0] = rec.normal[0]; f.n[1] = rec.normal[1]; f.n[2] = rec.normal[2]; f.src = s_rsM[sm] + smi;
+                    f.o[0] = rec.v0[0]; f.o[1] = rec.v0[1]; f.o[2] = rec.v0[2]; f.kept = rec.kept;
+                    frozen[(size_t)blockIdx.y * frozen_stride + q] = f;
+                }
                 if (corr && (corr_stride > 0 || ps == NP - 1)) {      // corr_stride > 0: the records of EVERY pass, [pass][corr_stride]
 #pragma unroll
                     for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
@@ -504,12 +511,12 @@ __global__ void __launch_bounds__(256) k_neq_reduce(DevBuffers B, const IcpUnit 
 int launch_icp_runs_cap(int max_points) { return icp_runs_cap(max_points); }
 
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
-                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride) {
+                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride, IcpFrozen *frozen, int frozen_stride) {
     if (n_units <= 0) return;
     const int runs_cap = icp_runs_cap(B.N);
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
-    k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride);
+    k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
     if (L.post) L.post(L.user, VK_ICP_PASS);
     dim3 g2(n_units, n_pass);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);

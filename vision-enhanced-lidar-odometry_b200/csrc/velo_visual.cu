@@ -42,9 +42,12 @@ __global__ void __launch_bounds__(VIS_THREADS, VIS_MIN_BLOCKS) k_visual(DevBuffe
     const VisUnit U = units[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int C = cal.num_cams, MM = B.MM, iter = U.iter;
-    if (fx.done && *fx.done) return;                 // device-side solver already converged: nothing to evaluate
+    const LmState *lm = fx.lm ? fx.lm + blockIdx.y : nullptr;
+    if (lm && !fx.use_accepted && lm->done) return;  // device-side solver of this unit already converged: nothing to evaluate
     if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-    if (tid < 6) s_pose[tid] = fx.pose ? fx.pose[tid] : U.pose[tid];
+    if (tid < 6) s_pose[tid] = lm ? (fx.use_accepted ? lm->x[tid] : lm->xt[tid]) : U.pose[tid];
+    const unsigned char *sel_in = fx.sel_in ? fx.sel_in + (size_t)blockIdx.y * fx.sel_stride : nullptr;
+    unsigned char *sel_out = fx.sel_out ? fx.sel_out + (size_t)blockIdx.y * fx.sel_stride : nullptr;
     __syncthreads();
     if (tid < 6) rotpack_column(s_pose, tid >= 3, tid % 3, &s_rp[tid >= 3]);
     __syncthreads();
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(VIS_THREADS, VIS_MIN_BLOCKS) k_visual(DevBuffe
                 // Free mode: the reference's selection + iter>1 outlier gates (velo.h:662-789); the chosen types are optionally
                 // recorded as a bit mask (1 = 3D3D, 2 = 2D2D, 4 = 3D2D, 8 = 2D3D).  Fixed mode (fx.sel_in): the block list was
                 // frozen by an earlier call (what ceres::Solve sees: AddResidualBlock happened before), so no gate is applied.
-                fixed = fx.sel_in ? (unsigned)fx.sel_in[lmi] | 0x100u : 0u;
+                fixed = sel_in ? (unsigned)sel_in[lmi] | 0x100u : 0u;
             }
         }
         VisMatchOut *mo = (mout && ok) ? &mout[lmi] : nullptr;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(VIS_THREADS, VIS_MIN_BLOCKS) k_visual(DevBuffe
             for (int row = 0; row < 2; row++) neq_mma_rows(S, lane, J + 6 * row, r[row], rho1, emit, cr0, cr1, cw0, cw1);
         }
         if (emit) { cost_half += 0.5 * rho0; nblk++; nres += 2; }
-        if (ok && fx.sel_out) fx.sel_out[lmi] = (unsigned char)chosen;
+        if (ok && sel_out) sel_out[lmi] = (unsigned char)chosen;
         if (mo) mo->n = nb;
     }
     for (int o = 16; o > 0; o >>= 1) { nblk += __shfl_down_sync(FULL, nblk, o); nres += __shfl_down_sync(FULL, nres, o); }
@@ -157,9 +160,10 @@ __global__ void __launch_bounds__(VIS_THREADS, VIS_MIN_BLOCKS) k_visual(DevBuffe
     if (tid == 0) { pout[56] = (double)s_cnt[0]; pout[57] = (double)s_cnt[1]; pout[58] = (double)(e1 > e0 ? e1 - e0 : 0); }
 }
 
-__global__ void k_neq_reduce_vis(const double *__restrict__ partial, double *__restrict__ out, int ctas) {
+__global__ void k_neq_reduce_vis(const double *__restrict__ partial, double *__restrict__ out, int ctas, const LmState *__restrict__ lm, int use_accepted) {
     const int u = blockIdx.x, t = threadIdx.x;
     if (t >= VELO_NEQ_STRIDE) return;
+    if (lm && !use_accepted && lm[u].done) return;   // the partials of a converged unit are stale; its last sums stay
     double s = 0.0;
     if (t < 59) for (int c = 0; c < ctas; c++) s += partial[((size_t)u * ctas + c) * 64 + t];
     out[(size_t)u * VELO_NEQ_STRIDE + t] = s;
@@ -173,6 +177,6 @@ void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, 
     k_visual<<<g, VIS_THREADS, 0, L.stream>>>(B, cal, units, tun, lm_valid, lm_xyz, partial, match_out, fx, bad_flag);
     if (L.post) L.post(L.user, VK_VISUAL);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);
-    k_neq_reduce_vis<<<n_units, 64, 0, L.stream>>>(partial, out, ctas);
+    k_neq_reduce_vis<<<n_units, 64, 0, L.stream>>>(partial, out, ctas, fx.lm, fx.use_accepted);
     if (L.post) L.post(L.user, VK_NEQ_REDUCE);
 }

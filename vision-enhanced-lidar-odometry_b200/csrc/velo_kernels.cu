@@ -94,6 +94,18 @@ __global__ void __launch_bounds__(256) k_ingest_permute(DevBuffers B, DevCalib c
 // distances / decisions are evaluated on the cam-0 coordinates exactly as the reference does.
 // one CTA per (ring, slot): counting sort of the ring by azimuth bin + per-sector elevation intervals.
 // Replaces the 64 KdTreeFLANN::setInputCloud calls of lru.h:17-20.
+// Angles come from atan2_q (|error| < 2e-6 rad, velo_common.cuh) instead of atan2f (a third of the instructions; the kernel was
+// instruction bound on three atan2f per point): the azimuth only decides a BIN, and the query's window is padded by 1e-5 rad for
+// exactly this (asin_ub); the elevation only feeds the sector boxes, which are widened by INDEX_EL_PAD here.  Bins are kept in
+// registers between the histogram pass and the scatter pass.
+#define INDEX_EL_PAD 4e-6f
+#define INDEX_KEEP 8          /* points per thread whose bin stays in a register (rings up to 2048 points) */
+__device__ __forceinline__ int index_bin_of(const DevCalib &cal, const float4 &p, float &el, float &rho) {
+    float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
+    const float dxy2 = vx * vx + vy * vy;
+    el = atan2_q(vz, sqrtf(dxy2)); rho = sqrtf(dxy2 + vz * vz);
+    return az_bin(atan2_q(vy, vx));
+}
 __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal, int slot0) {
     __shared__ int s_hist[VELO_AZ_BINS];
     __shared__ int s_cur[VELO_AZ_BINS];
@@ -107,17 +119,30 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
     for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) { s_hist[i] = 0; s_cur[i] = 0; }
     if (tid < VELO_SECTORS) { s_lo[tid] = s_rlo[tid] = f2ord(CUDART_INF_F); s_hi[tid] = s_rhi[tid] = f2ord(-CUDART_INF_F); }
     __syncthreads();
-    for (int i = tid; i < L; i += blockDim.x) {
-        float4 p = pts[i];
-        float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
-        int b = az_bin(atan2f(vy, vx));
-        const float dxy2 = vx * vx + vy * vy;
-        int e = f2ord(atan2f(vz, sqrtf(dxy2))), rr = f2ord(sqrtf(dxy2 + vz * vz));
-        atomicAdd(&s_hist[b], 1);
-        atomicMin(&s_lo[b / VELO_BINS_PER_SECTOR], e);
-        atomicMax(&s_hi[b / VELO_BINS_PER_SECTOR], e);
-        atomicMin(&s_rlo[b / VELO_BINS_PER_SECTOR], rr);
-        atomicMax(&s_rhi[b / VELO_BINS_PER_SECTOR], rr);
+    int bins[INDEX_KEEP];
+    for (int i0 = 0; i0 < L; i0 += 256 * INDEX_KEEP) {               // (one trip for every real ring)
+#pragma unroll
+        for (int k = 0; k < INDEX_KEEP; k++) {
+            const int i = i0 + tid + 256 * k;
+            int b = -1, e = 0, rr = 0;
+            if (i < L) {
+                float el, rho;
+                b = index_bin_of(cal, pts[i], el, rho);
+                e = f2ord(el); rr = f2ord(rho);
+                atomicAdd(&s_hist[b], 1);
+            }
+            if (i0 == 0) bins[k] = b;
+            // sector bounds: lanes of a warp hold consecutive points, i.e. mostly one sector -> reduce inside the warp first
+            const unsigned act = __ballot_sync(FULL, i < L);
+            if (i < L) {
+                const int sec = b / VELO_BINS_PER_SECTOR;
+                const unsigned grp = __match_any_sync(act, sec);
+                const int elo = __reduce_min_sync(grp, e), ehi = __reduce_max_sync(grp, e), rlo = __reduce_min_sync(grp, rr), rhi = __reduce_max_sync(grp, rr);
+                if ((int)(__ffs(grp) - 1) == (tid & 31)) {
+                    atomicMin(&s_lo[sec], elo); atomicMax(&s_hi[sec], ehi); atomicMin(&s_rlo[sec], rlo); atomicMax(&s_rhi[sec], rhi);
+                }
+            }
+        }
     }
     __syncthreads();
     // exclusive scan of the AZ bins with 256 threads (AZ/256 consecutive bins each)
@@ -132,16 +157,24 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
     int *cs = B.cell_start + ((size_t)slot * B.R + ring) * (VELO_AZ_BINS + 1);
     for (int i = tid; i < VELO_AZ_BINS; i += blockDim.x) cs[i] = r0 + s_hist[i];
     if (tid == 0) cs[VELO_AZ_BINS] = r0 + L;
-    if (tid < VELO_SECTORS)
-        B.sec_box[((size_t)slot * B.R + ring) * VELO_SECTORS + tid] = make_float4(ord2f(s_lo[tid]), ord2f(s_hi[tid]), ord2f(s_rlo[tid]), ord2f(s_rhi[tid]));
+    if (tid < VELO_SECTORS) {                                          // (an empty sector keeps lo = +inf > hi = -inf)
+        const float lo = ord2f(s_lo[tid]), hi = ord2f(s_hi[tid]);
+        B.sec_box[((size_t)slot * B.R + ring) * VELO_SECTORS + tid] = make_float4(lo - INDEX_EL_PAD, hi + INDEX_EL_PAD, ord2f(s_rlo[tid]), ord2f(s_rhi[tid]));
+    }
     float4 *sorted = B.sorted + (size_t)slot * B.N + r0;
-    for (int i = tid; i < L; i += blockDim.x) {
-        float4 p = pts[i];
-        float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
-        int b = az_bin(atan2f(vy, vx));
-        int pos = s_hist[b] + atomicAdd(&s_cur[b], 1);
-        p.w = __int_as_float(i);
-        sorted[pos] = p;
+    for (int i0 = 0; i0 < L; i0 += 256 * INDEX_KEEP) {
+#pragma unroll
+        for (int k = 0; k < INDEX_KEEP; k++) {
+            const int i = i0 + tid + 256 * k;
+            if (i < L) {
+                float4 p = pts[i];
+                float el, rho;
+                const int b = (i0 == 0) ? bins[k] : index_bin_of(cal, p, el, rho);
+                const int pos = s_hist[b] + atomicAdd(&s_cur[b], 1);
+                p.w = __int_as_float(i);
+                sorted[pos] = p;
+            }
+        }
     }
 }
 
@@ -335,12 +368,16 @@ __device__ __forceinline__ bool width_ok(float dx, const DevCalib &cal) {   // h
 // The ring loop, bracket search and bilinear patch of velo.h:390-492 (H4/H5), one thread per keypoint.
 // One CTA per (camera, slot) serves every keypoint set of that image: the projections of all rings (x,y pairs, ~140 KB for a
 // KITTI frame) are first staged in shared memory, because the searches are scattered 8-byte reads.
-//  * Which rings a keypoint has to search is read from a table: for each of ASSOC_YB buckets of the image height, the bit mask of
-//    the rings that can take part in a hit for a keypoint with y in that bucket.  A hit on the ring pair (s-1, s) needs
-//    (proj[s][mid].y > kp.y) != (proj[s-1][last].y > kp.y) (velo.h:414-415): impossible when both rings lie entirely above
-//    (y > kp.y everywhere) or entirely not-above.  A ring whose two pairs are both impossible cannot influence the result, so it is
-//    not searched and `last` is -1 after it, exactly as after a ring without a bracket (the mask is a conservative superset:
-//    evaluated at both bucket edges; searching a ring that was not needed is what the reference does anyway).
+//  * Which rings a keypoint has to search is read from a table.  A hit on the ring pair (s-1, s) needs
+//    (proj[s][mid].y > kp.y) != (proj[s-1][last].y > kp.y) (velo.h:414-415): impossible when, over the points that can be those
+//    bracket ends, both rings lie above the keypoint (y > kp.y) or both lie not-above.  A ring whose two pairs are both
+//    impossible cannot influence the result, so it is not searched and `last` is -1 after it, exactly as after a ring without
+//    a bracket (searching a ring that was not needed is what the reference does anyway, so any superset is exact).
+//    1-D table (always): per bucket of the image height, the rings needed judging by each ring's whole y range.
+//    2-D table (<= 64 rings, float `abs`): per (y bucket, x zone).  The width gate (velo.h:416-421) only lets a bracket hit if its
+//    two ends are closer than depth_assoc_thresh in x, and the keypoint lies between them, so both ends are within the threshold
+//    of kp.x: only a ring's points inside the zone widened by the threshold count for its y range.  Rings are smooth curves in
+//    the image, so this leaves the two or three rings around the keypoint instead of the dozen whose full y range covers it.
 //  * The reference's binary search (velo.h:404-412) finds an index mid with proj[mid].x <= kp.x < proj[mid+1].x.  On a ring whose
 //    projected x never decreases (every ring, unless the occlusion stack pushed a z-tie, velo.h:360-366) that index is unique —
 //    the last point with x <= kp.x — so ANY search finds the reference's bracket.  Such rings get a 128-bucket x table while they
@@ -348,26 +385,37 @@ __device__ __forceinline__ bool width_ok(float dx, const DevCalib &cal) {   // h
 //    strictly right, because the bucket function is monotone) and the search is two table reads plus a scan of the keypoint's own
 //    bucket (~2 points) instead of 9 dependent steps.  A ring with a decreasing x (H4), a NaN keypoint, or a projection that does
 //    not fit in shared memory takes the reference's exact sequence of mid points.
+// Staging, the x tables and the zone ranges are built with one warp per ring (lanes stride over the ring's points).
 #ifndef ASSOC_THREADS
-#define ASSOC_THREADS 1024         /* measured 512 -> 1024: 0.303 -> 0.252 ms per 200 frames (more keypoints in flight per staged image) */
+#define ASSOC_THREADS 1024        /* measured 512 -> 1024: 0.303 -> 0.252 ms per 200 frames (more keypoints in flight per staged image) */
 #endif
-#define ASSOC_DYN_BYTES (200 * 1024)   /* dynamic shared memory: staged (x,y) pairs + the x tables */
-#define ASSOC_YB 256                   /* keypoint-y buckets of the needed-ring table */
+#define ASSOC_DYN_BYTES (200 * 1024)   /* dynamic shared memory: staged (x,y) pairs + the x tables + the 2-D ring table (+ 24 KB static <= 227 KB) */
+#define ASSOC_YB 256                   /* keypoint-y buckets of the needed-ring tables */
 #define ASSOC_NB 128                   /* x buckets per ring */
+#define ASSOC_ZONES 16                 /* x zones of the 2-D needed-ring table */
+#define ASSOC_MAXW (VELO_MAX_RINGS_HARD / 64)
 __device__ __forceinline__ int assoc_xbucket(float x, float xmin, float xscale) {   // monotone non-decreasing in x (NaN -> 0)
     const int b = (int)((x - xmin) * xscale);
     return min(max(b, 0), ASSOC_NB - 1);
 }
+__device__ __forceinline__ int assoc_zone(float x, float xmin, float zscale) {      // monotone non-decreasing in x
+    const int z = (int)((x - xmin) * zscale);
+    return min(max(z, 0), ASSOC_ZONES - 1);
+}
+__device__ __forceinline__ int assoc_ybucket(float y, float ymin, float yscale) { return min(max((int)((y - ymin) * yscale), 0), ASSOC_YB - 1); }
 __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, DevCalib cal, int slot0, int set0, int nsets, int cam0) {
     extern __shared__ float2 s_proj[];
     __shared__ int s_off[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_rs[VELO_MAX_RINGS_HARD + 1];
     __shared__ int s_cnt[VELO_MAX_RINGS_HARD];
     __shared__ float2 s_yr[VELO_MAX_RINGS_HARD];
+    __shared__ float2 s_pair[VELO_MAX_RINGS_HARD + 1];   // pair (p-1, p): a keypoint can hit it only if s_pair[p].x <= kp.y < s_pair[p].y
     __shared__ int s_mono[VELO_MAX_RINGS_HARD];
-    __shared__ unsigned long long s_need[ASSOC_YB + 1][VELO_MAX_RINGS_HARD / 64];   // [ASSOC_YB]: every searchable ring (keypoints outside the image)
+    __shared__ unsigned long long s_need[ASSOC_YB + 1][ASSOC_MAXW];   // [ASSOC_YB]: every searchable ring (keypoints outside the image)
+    __shared__ int2 s_zr[64][ASSOC_ZONES];                            // y range (ordered ints) of ring s inside zone z widened by the width gate
     __shared__ int s_w[33];
     const int cam = cam0 + blockIdx.x, slot = slot0 + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
     const int nr = B.n_rings[slot], NW = (nr + 63) >> 6;
     const int *rs = B.ring_start + (size_t)slot * (B.R + 1);
     const int *pc = B.proj_count + ((size_t)slot * B.C + cam) * B.R;
@@ -376,7 +424,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
     const float4 *valid = B.valid + ((size_t)slot * B.C + cam) * B.N;
     int total = 0;
     for (int i0 = 0; i0 < nr; i0 += blockDim.x) {                 // ring offsets in the staged array (exclusive scan of the counts)
-        const int i = i0 + threadIdx.x;
+        const int i = i0 + tid;
         const int c = i < nr ? pc[i] : 0;
         if (i < nr) { s_rs[i] = rs[i]; s_cnt[i] = c; s_yr[i] = yr[i]; s_mono[i] = 1; }
         int t;
@@ -384,53 +432,98 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
         if (i < nr) s_off[i] = total + ex;
         total += t;
     }
-    if (threadIdx.x == 0) s_off[nr] = total;
+    if (tid == 0) s_off[nr] = total;
+    for (int i = tid; i < 64 * ASSOC_ZONES; i += blockDim.x) (&s_zr[0][0])[i] = make_int2(f2ord(CUDART_INF_F), f2ord(-CUDART_INF_F));
+    for (int i = tid; i < (ASSOC_YB + 1) * ASSOC_MAXW; i += blockDim.x) (&s_need[0][0])[i] = 0ull;
     __syncthreads();
+    const size_t b_pts = (size_t)total * sizeof(float2), b_lut = ((size_t)nr * (ASSOC_NB + 1) * sizeof(unsigned short) + 15) & ~(size_t)15;
     unsigned short *s_lut = reinterpret_cast<unsigned short *>(s_proj + total);
-    const bool fits = (size_t)total * sizeof(float2) + (size_t)nr * (ASSOC_NB + 1) * sizeof(unsigned short) <= ASSOC_DYN_BYTES;
-    const float xmin = cal.fov[cam][0], xscale = ASSOC_NB / (cal.fov[cam][1] - cal.fov[cam][0]);
+    unsigned long long *s_need2 = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(s_proj) + ((b_pts + b_lut + 15) & ~(size_t)15));   // [ASSOC_YB][ASSOC_ZONES]
+    const bool fits = b_pts + b_lut + 16 <= ASSOC_DYN_BYTES;
+    const bool use2d = fits && nr <= 64 && !cal.abs_truncates &&
+                       b_pts + b_lut + 32 + (size_t)ASSOC_YB * ASSOC_ZONES * sizeof(unsigned long long) <= ASSOC_DYN_BYTES;
+    const float xmin = cal.fov[cam][0], xspan = cal.fov[cam][1] - cal.fov[cam][0], xscale = ASSOC_NB / xspan, zscale = ASSOC_ZONES / xspan;
+    const float ymin = cal.fov[cam][2], ymax = cal.fov[cam][3], yscale = ASSOC_YB / (ymax - ymin);
+    const float zpad = cal.assoc_thr * 1.01f + 1e-6f;             // the width gate: bracket ends lie within assoc_thr of the keypoint in x
+    if (use2d) for (int i = tid; i < ASSOC_YB * ASSOC_ZONES; i += blockDim.x) s_need2[i] = 0ull;
     if (fits) {
-        // 8-byte cp.async per projection: no register round trip, so the copies of all rings are in flight together
-        for (int s = 0; s < nr; s++) {
+        // one warp per ring: 8-byte cp.async per projection (no register round trip; all rings in flight together)
+        for (int s = wid; s < nr; s += nwarps) {
             const float2 *src = proj + s_rs[s];
             const unsigned dst = (unsigned)__cvta_generic_to_shared(s_proj + s_off[s]);
-            for (int i = threadIdx.x; i < s_cnt[s]; i += blockDim.x)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(src + i) : "memory");
+            const int cnt = s_cnt[s];
+            for (int i = lane; i < cnt; i += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(src + i) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // x tables: lut[s][b] = first index of ring s whose bucket is >= b (points are bucket-sorted on a ring with non-decreasing x);
-        // a decreasing x marks the ring for the exact search
-        for (int s = 0; s < nr; s++) {
+        // a decreasing x marks the ring for the exact search.  Zone ranges: warp-reduced per zone before they go to shared memory.
+        for (int s = wid; s < nr; s += nwarps) {
             const float2 *ps = s_proj + s_off[s];
             unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
             const int cnt = s_cnt[s];
-            for (int i = threadIdx.x; i <= cnt; i += blockDim.x) {
-                const float xp = i > 0 ? ps[i - 1].x : 0.f, xi = i < cnt ? ps[i].x : 0.f;
-                const int bp = i > 0 ? assoc_xbucket(xp, xmin, xscale) : -1, bi = i < cnt ? assoc_xbucket(xi, xmin, xscale) : ASSOC_NB;
-                if (i > 0 && i < cnt && xp > xi) s_mono[s] = 0;
-                for (int b = bp + 1; b <= bi; b++) lut[b] = (unsigned short)i;
+            for (int i0 = 0; i0 <= cnt; i0 += 32) {
+                const int i = i0 + lane;
+                const bool in = i < cnt;
+                const float2 pi = in ? ps[i] : make_float2(0.f, 0.f);
+                if (i <= cnt) {
+                    const float xp = i > 0 ? ps[i - 1].x : 0.f;
+                    const int bp = i > 0 ? assoc_xbucket(xp, xmin, xscale) : -1, bi = in ? assoc_xbucket(pi.x, xmin, xscale) : ASSOC_NB;
+                    if (i > 0 && in && xp > pi.x) s_mono[s] = 0;
+                    for (int b = bp + 1; b <= bi; b++) lut[b] = (unsigned short)i;
+                }
+                if (use2d) {
+                    // a point counts for every zone a keypoint within the width gate of it can fall in (1 or 2 zones)
+                    const int z0 = assoc_zone(pi.x - zpad, xmin, zscale), z1 = assoc_zone(pi.x + zpad, xmin, zscale), yo = f2ord(pi.y);
+                    const unsigned act = __ballot_sync(FULL, in);
+                    if (in) {
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int z = k == 0 ? z0 : z1;
+                            const unsigned grp = __match_any_sync(act, z);
+                            const int lo = __reduce_min_sync(grp, yo), hi = __reduce_max_sync(grp, yo);
+                            if ((int)(__ffs(grp) - 1) == lane && (k == 0 || z1 != z0)) { atomicMin(&s_zr[s][z].x, lo); atomicMax(&s_zr[s][z].y, hi); }
+                        }
+                        for (int z = z0 + 1; z < z1; z++) { atomicMin(&s_zr[s][z].x, yo); atomicMax(&s_zr[s][z].y, yo); }   // (zones narrower than the gate: never with 16 zones)
+                    }
+                }
             }
         }
     }
-    // needed-ring masks per keypoint-y bucket
-    const float ymin = cal.fov[cam][2], ymax = cal.fov[cam][3], yscale = ASSOC_YB / (ymax - ymin);
-    for (int bkt = threadIdx.x; bkt <= ASSOC_YB; bkt += blockDim.x) {
+    // 1-D table.  Pair (a, b) is impossible for a keypoint iff (ymin_a > y && ymin_b > y) || (ymax_a <= y && ymax_b <= y), i.e. possible
+    // iff min(ymin_a, ymin_b) <= y < max(ymax_a, ymax_b); ring s is needed iff pair (s-1, s) or pair (s, s+1) is possible.
+    for (int p = tid; p <= nr; p += blockDim.x) {
+        float2 pr = make_float2(CUDART_INF_F, -CUDART_INF_F);        // pairs with a ring that does not exist are impossible
+        if (p > 0 && p < nr) pr = make_float2(fminf(s_yr[p - 1].x, s_yr[p].x), fmaxf(s_yr[p - 1].y, s_yr[p].y));
+        s_pair[p] = pr;
+    }
+    __syncthreads();
+    for (int bkt = tid; bkt <= ASSOC_YB; bkt += blockDim.x) {
         const float y0 = ymin + bkt / yscale - 1e-4f, y1 = ymin + (bkt + 1) / yscale + 1e-4f;   // bucket edges, padded
 #pragma unroll
-        for (int w = 0; w < VELO_MAX_RINGS_HARD / 64; w++) {
+        for (int w = 0; w < ASSOC_MAXW; w++) {
             unsigned long long m = 0ull;
             for (int s2 = 64 * w; s2 < min(nr, 64 * w + 64); s2++) {
-                // pair (a,b) impossible for all y in the bucket if (ymin_a > y1 && ymin_b > y1) || (ymax_a <= y0 && ymax_b <= y0)
-                auto imp = [&](int a2, int b2) -> bool {
-                    if (a2 < 0 || b2 >= nr) return true;
-                    return (s_yr[a2].x > y1 && s_yr[b2].x > y1) || (s_yr[a2].y <= y0 && s_yr[b2].y <= y0);
-                };
-                const bool need = bkt == ASSOC_YB || !(imp(s2 - 1, s2) && imp(s2, s2 + 1));
+                const float2 pa = s_pair[s2], pb = s_pair[s2 + 1];
+                const bool need = bkt == ASSOC_YB || (pa.x <= y1 && y0 < pa.y) || (pb.x <= y1 && y0 < pb.y);
                 if (need && s_cnt[s2] > 1) m |= 1ull << (s2 & 63);                               // rings with <= 1 points: velo.h:400-403
             }
             s_need[bkt][w] = m;
+        }
+    }
+    // 2-D table: one thread per (pair, zone) marks both rings of the pair in the y buckets the pair can be hit from in that zone
+    if (use2d) {
+        for (int t = tid; t < nr * ASSOC_ZONES; t += blockDim.x) {
+            const int p = t / ASSOC_ZONES + 1, z = t % ASSOC_ZONES;      // pair (p-1, p), p = 1 .. nr-1
+            if (p >= nr || s_cnt[p - 1] <= 1 || s_cnt[p] <= 1) continue;
+            const int2 ra = s_zr[p - 1][z], rb = s_zr[p][z];
+            if (ra.x > ra.y || rb.x > rb.y) continue;                    // a ring without points near the zone cannot close a bracket there
+            const float lo = fminf(ord2f(ra.x), ord2f(rb.x)), hi = fmaxf(ord2f(ra.y), ord2f(rb.y));
+            if (!(hi >= ymin) || !(lo < ymax)) continue;
+            const int b0 = assoc_ybucket(lo - 2e-4f, ymin, yscale), b1 = assoc_ybucket(hi + 2e-4f, ymin, yscale);
+            const unsigned long long bits = (1ull << (p - 1)) | (1ull << p);
+            for (int bkt = b0; bkt <= b1; bkt++) atomicOr(&s_need2[bkt * ASSOC_ZONES + z], bits);
         }
     }
     __syncthreads();
@@ -439,16 +532,19 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
     for (int si = 0; si < nsets; si++) {
         const size_t sc = ((size_t)slot * VELO_NUM_KP_SETS + (set0 + si)) * B.C + cam;
         const int F = B.n_kp[sc];
-        for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        for (int k = tid; k < F; k += blockDim.x) {
             const float2 kp = B.kp[sc * B.F + k];
-            const int bkt = (kp.y >= ymin && kp.y < ymax) ? min(max((int)((kp.y - ymin) * yscale), 0), ASSOC_YB - 1) : ASSOC_YB;
-            const bool kx_ok = kp.x == kp.x;
+            const bool y_in = kp.y >= ymin && kp.y < ymax, kx_ok = kp.x == kp.x;
+            const int bkt = y_in ? assoc_ybucket(kp.y, ymin, yscale) : ASSOC_YB;
             const int xb = assoc_xbucket(kp.x, xmin, xscale);
+            const bool two_d = use2d && y_in && kx_ok;
             int last = -1, prev_s = -2, hit = 0;
             int h_s = 0, h_mid = 0, h_last = 0;          // the bracket of the hit; its interpolation (global gathers) runs after the search
             float2 pa = make_float2(0.f, 0.f), pb = pa;  // bracket of the previous ring
             for (int w = 0; w < NW && !hit; w++) {
-                for (unsigned long long m = s_need[bkt][w]; m && !hit; m &= m - 1) {
+                unsigned long long m = s_need[bkt][w];
+                if (two_d) m &= s_need2[bkt * ASSOC_ZONES + assoc_zone(kp.x, xmin, zscale)];
+                for (; m && !hit; m &= m - 1) {
                     const int s = (w << 6) + __ffsll((long long)m) - 1;
                     if (s != prev_s + 1) last = -1;                                  // a ring that was not searched lies in between
                     prev_s = s;

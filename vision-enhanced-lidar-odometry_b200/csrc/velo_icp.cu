@@ -328,6 +328,37 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         s_cur = s; have = true; best = scan_init(thr_excl);
                     }
                     if (!__any_sync(FULL, have)) break;
+#ifdef ICP_PAIR
+                    // Lane pairing: a round lasts as long as its longest range, so the lane 16 away (a query 16 points further along the
+                    // ring: a different surface often enough) takes the tail half of the surplus of a longer range, evaluates it against
+                    // the owner's query, and hands the best key back.  The set of evaluated candidates is unchanged: exact.
+                    {
+                        if (have && p0 >= e0) { p0 = p1; e0 = e1; p1 = 0; e1 = 0; }
+                        const bool simple = !have || p1 >= e1;                       // a wrapped window keeps its own work
+                        const int len = (have && simple) ? max(e0 - p0, 0) : 0;
+                        const int olen = __shfl_xor_sync(FULL, len, 16), oe0 = __shfl_xor_sync(FULL, e0, 16);
+                        const float omx = __shfl_xor_sync(FULL, mx, 16), omy = __shfl_xor_sync(FULL, my, 16), omz = __shfl_xor_sync(FULL, mz, 16);
+                        const bool both = simple && __shfl_xor_sync(FULL, (int)simple, 16);
+                        const int d = len - olen;
+                        const int give = (both && d >= ICP_PAIR) ? (d >> 1) : 0, take = (both && -d >= ICP_PAIR) ? ((-d) >> 1) : 0;
+                        u64 xbest = scan_init(thr_excl);
+                        if (have) {
+                            scan_range(sorted, p0, e0 - give, mx, my, mz, best, st_exh);
+                            p0 = e0;
+                        }
+                        scan_range(sorted, oe0 - take, take > 0 ? oe0 : oe0 - take, omx, omy, omz, xbest, st_exh);
+                        const u64 back = __shfl_xor_sync(FULL, xbest, 16);
+                        if (give > 0) best = min(best, back);
+                        if (have && p1 >= e1) {                              // ring finished
+                            st_rings++; have = false;
+                            if (scan_found(best, thr_excl)) {
+                                const u64 oj = kj;
+                                merge_key(scan_key(best, s_cur), ki, kj);
+                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
+                            }
+                        }
+                    }
+#else
                     if (have) {
                         // at most ICP_SCAN_CHUNK candidates per round: lanes with long ranges continue in the next round while
                         // the others already advance to their next ring, which keeps the distance loop's trip counts uniform
@@ -344,6 +375,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                             }
                         }
                     }
+#endif
                 }
             }
             if (active) {
@@ -398,6 +430,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         kept = true;
                     }
                 }
+#ifndef EXP_NO_RECORDS
                 if (frozen && ps == NP - 1) {      // compact record for the device-resident solve (two 16-byte stores)
                     IcpFrozen f;
                     f.n[0] = rec.normal[0]; f.n[1] = rec.normal[1]; f.n[2] = rec.normal[2]; f.src = s_rsM[sm] + smi;
@@ -412,6 +445,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #endif
                     corr[(size_t)(corr_stride > 0 ? ps : 0) * corr_stride + q] = rec;
                 }
+#endif
             }
             // ---- normal equations of this pass: rows of the 32 lanes -> the 28+28 sums of the (pass, warp) record
 #ifndef EXP_NO_ACCUM

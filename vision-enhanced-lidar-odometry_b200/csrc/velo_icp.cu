@@ -147,6 +147,9 @@ __device__ __forceinline__ u64 ring_mask(const u64 *__restrict__ mlo, const u64 
 __host__ __device__ inline int icp_blocks(int queries) { return (queries + ICP_BLOCK_QUERIES - 1) / ICP_BLOCK_QUERIES; }
 __host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(max_points) * ICP_WARPS; }
 
+// RECORDS = false: the throughput instantiation of the batched front end (no per-query records are written; 1.3 % faster than
+// carrying the dead record code)
+template <bool RECORDS>
 __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
                                                           double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
                                                           IcpFrozen *__restrict__ frozen, int frozen_stride) {
@@ -185,7 +188,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
     const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
+#ifdef EXP_FORCE_W1      /* timing experiment: ring masks of one 64-bit word known at compile time (valid for <= 64 rings only) */
+    const int W = 1;
+#else
     const int W = B.W;
+#endif
     const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *rloS = B.rmask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
@@ -338,7 +345,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         const int len = (have && simple) ? max(e0 - p0, 0) : 0;
                         const int olen = __shfl_xor_sync(FULL, len, 16), oe0 = __shfl_xor_sync(FULL, e0, 16);
                         const float omx = __shfl_xor_sync(FULL, mx, 16), omy = __shfl_xor_sync(FULL, my, 16), omz = __shfl_xor_sync(FULL, mz, 16);
-                        const bool both = simple && __shfl_xor_sync(FULL, (int)simple, 16);
+                        const int osimple = __shfl_xor_sync(FULL, (int)simple, 16);      // (not inside the && below: every lane must take part)
+                        const bool both = simple && osimple != 0;
                         const int d = len - olen;
                         const int give = (both && d >= ICP_PAIR) ? (d >> 1) : 0, take = (both && -d >= ICP_PAIR) ? ((-d) >> 1) : 0;
                         u64 xbest = scan_init(thr_excl);
@@ -430,14 +438,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         kept = true;
                     }
                 }
-#ifndef EXP_NO_RECORDS
-                if (frozen && ps == NP - 1) {      // compact record for the device-resident solve (two 16-byte stores)
+                if (RECORDS && frozen && ps == NP - 1) {      // compact record for the device-resident solve (two 16-byte stores)
                     IcpFrozen f;
                     f.n[0] = rec.normal[0]; f.n[1] = rec.normal[1]; f.n[2] = rec.normal[2]; f.src = s_rsM[sm] + smi;
                     f.o[0] = rec.v0[0]; f.o[1] = rec.v0[1]; f.o[2] = rec.v0[2]; f.kept = rec.kept;
                     frozen[(size_t)blockIdx.y * frozen_stride + q] = f;
                 }
-                if (corr && (corr_stride > 0 || ps == NP - 1)) {      // corr_stride > 0: the records of EVERY pass, [pass][corr_stride]
+                if (RECORDS && corr && (corr_stride > 0 || ps == NP - 1)) {      // corr_stride > 0: the records of EVERY pass, [pass][corr_stride]
 #pragma unroll
                     for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
 #ifdef VELO_ICP_DEBUG   /* tools/icp_debug_hist.py: per-query search statistics instead of the Jacobian */
@@ -445,7 +452,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #endif
                     corr[(size_t)(corr_stride > 0 ? ps : 0) * corr_stride + q] = rec;
                 }
-#endif
             }
             // ---- normal equations of this pass: rows of the 32 lanes -> the 28+28 sums of the (pass, warp) record
 #ifndef EXP_NO_ACCUM
@@ -550,7 +556,8 @@ void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, con
     const int runs_cap = icp_runs_cap(B.N);
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
-    k_icp_pass<<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    if (corr || frozen) k_icp_pass<true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    else k_icp_pass<false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, nullptr, 0, nullptr, 0);
     if (L.post) L.post(L.user, VK_ICP_PASS);
     dim3 g2(n_units, n_pass);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);

@@ -272,15 +272,15 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 }
                 // Phase 1 (probe), only while two rings do not yet hold a candidate: rings in order of increasing elevation
                 // gap (levels of doubling tolerance, read from the ring masks), only the query's own azimuth bin of each.
-#ifdef EXP_NO_PROBE
-                if (false) {
-#else
-                if (kj == KEY_INF) {
+#ifndef ICP_PROBE_LEVELS
+#define ICP_PROBE_LEVELS 64        /* levels of doubling elevation tolerance the probe may use (0 = no probe) */
 #endif
+                if (ICP_PROBE_LEVELS > 0 && kj == KEY_INF) {
                     const float gam_thr = make_window(thr_f, az, D, rho).gam;   // elevation tolerance of the threshold itself
                     Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq;
                     u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                    for (float lev = 0.0065f; kj == KEY_INF; lev *= 2.0f) {
+                    int nlev = 0;
+                    for (float lev = 0.0065f; kj == KEY_INF && nlev < ICP_PROBE_LEVELS; lev *= 2.0f, nlev++) {
                         ws.gam = fminf(lev, gam_thr);
 #pragma unroll
                         for (int word = 0; word < 4; word++) {
@@ -433,7 +433,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
                         const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
                         rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
+#ifdef ICP_LOG_PROD
+                        rho0h = sum;                 // the warp multiplies the 32 arguments and takes ONE logarithm (see the accumulation)
+#else
                         rho0h = 0.5 * U.weight * bb * log(sum);
+#endif
                         rec.kept = 1; rec.residual = res;
                         kept = true;
                     }
@@ -474,9 +478,18 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cr0), "+d"(cr1) : "d"(x), "d"(x));
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cw0), "+d"(cw1) : "d"(x), "d"(xw));
                 }
+#ifdef ICP_LOG_PROD
+                // sum of rho/2 = w a^2 / 2 * sum_i log(1 + r_i^2 / a^2) = w a^2 / 2 * log(prod_i (1 + r_i^2 / a^2)); each factor is in
+                // [1, 1 + thr / a^2] (<= 51 for the reference's constants), so the product of 32 cannot overflow
+                double ch = kept ? rho0h : 1.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ch *= __shfl_xor_sync(FULL, ch, o);
+                ch = 0.5 * U.weight * U.loss_a * U.loss_a * log(ch);
+#else
                 double ch = kept ? rho0h : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ch += __shfl_xor_sync(FULL, ch, o);
+#endif
                 // lane holds C[fr][2 fk], C[fr][2 fk + 1]; upper triangle -> record slots (H row-major upper, then g, then cost)
                 double *rec = s_acc[wid][ps];
                 const int c0 = 2 * fk, c1 = c0 + 1;

@@ -27,6 +27,15 @@
 #ifndef ICP_UNROLL
 #define ICP_UNROLL 4           /* candidate loads in flight per lane */
 #endif
+#ifndef ICP_TIGHT
+#define ICP_TIGHT 0.03f        /* elevation tolerance (rad) up to which a query's ring set is taken in one mask level */
+#endif
+#ifndef ICP_LEV0
+#define ICP_LEV0 0.0065f       /* first elevation-tolerance level of a query that is not tight (about one ring spacing) */
+#endif
+#ifndef ICP_LEVMUL
+#define ICP_LEVMUL 2.0f        /* growth of the tolerance from level to level */
+#endif
 #define VELO_STR_(x) #x
 #define VELO_UNROLL(n) _Pragma(VELO_STR_(unroll n))
 #define KEY_INF 0xFFFFFFFFFFFFFFFFull
@@ -93,16 +102,6 @@ __device__ __forceinline__ void scan_range(const float4 *__restrict__ sorted, in
 __device__ __forceinline__ u64 scan_init(float thr_excl) { return (u64)__float_as_uint(thr_excl) << 32; }
 __device__ __forceinline__ bool scan_found(u64 best, float thr_excl) { return (unsigned)(best >> 32) < __float_as_uint(thr_excl); }
 __device__ __forceinline__ u64 scan_key(u64 best, int s) { return (best & 0xFFFFFFFF00000000ull) | (u64)(((unsigned)s << VELO_IDX_BITS) | (unsigned)best); }
-__device__ __forceinline__ u64 scan_ring(const float4 *__restrict__ sorted, const int *__restrict__ cs, int s, const Window &w,
-                                         float mx, float my, float mz, float thr_excl, int &ncand) {
-    u64 best = scan_init(thr_excl);
-    if (!w.wrapped) scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + w.b1 + 1), mx, my, mz, best, ncand);
-    else {
-        scan_range(sorted, __ldg(cs + w.b0), __ldg(cs + VELO_AZ_BINS), mx, my, mz, best, ncand);
-        scan_range(sorted, __ldg(cs), __ldg(cs + w.b1 + 1), mx, my, mz, best, ncand);
-    }
-    return scan_found(best, thr_excl) ? scan_key(best, s) : KEY_INF;
-}
 // Candidate rings (64-ring word `word`) for a query at elevation el / range rho with search radius b: a ring qualifies in a
 // sector of the window if its elevation interval comes within w.gam of el AND its range interval within b of rho
 // (|q-p| >= |rq-rp| and |q-p| >= rq sin(angle), angle >= elevation gap).  Both tests are two loads from cumulative bucket
@@ -149,12 +148,17 @@ __host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(
 
 // RECORDS = false: the throughput instantiation of the batched front end (no per-query records are written; 1.3 % faster than
 // carrying the dead record code)
-template <bool RECORDS>
+// W1 = true: at most 64 rings, i.e. ring masks of ONE 64-bit word: the word loops and the visited-mask array disappear at compile
+// time (the array otherwise lives in local memory because it is indexed by a runtime word number; measured 4 % of the kernel).
+template <bool RECORDS, bool W1>
 __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
                                                           double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
                                                           IcpFrozen *__restrict__ frozen, int frozen_stride) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
+#ifdef ICP_RS_SMEM
+    __shared__ int s_rsS[VELO_MAX_RINGS_HARD + 1];
+#endif
     __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
     __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
     __shared__ unsigned long long s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];   // per warp: no atomics
@@ -171,6 +175,12 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const int skip = U.skip;
     for (int i = tid; i < (int)(NP * sizeof(IcpPass) / sizeof(double)); i += blockDim.x)
         reinterpret_cast<double *>(s_pass)[i] = reinterpret_cast<const double *>(U.pass)[i];
+#ifdef ICP_RS_SMEM
+    for (int i = tid; i <= B.n_rings[U.tgt_slot]; i += blockDim.x) s_rsS[i] = rsS[i];
+#define RS_S(i) s_rsS[i]
+#else
+#define RS_S(i) __ldg(rsS + (i))
+#endif
     for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 56; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
     for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0][0])[i] = 0ull;
     if (tid == 0) {
@@ -188,11 +198,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
     const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
-#ifdef EXP_FORCE_W1      /* timing experiment: ring masks of one 64-bit word known at compile time (valid for <= 64 rings only) */
-    const int W = 1;
-#else
-    const int W = B.W;
-#endif
+    const int W = W1 ? 1 : B.W;
     const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
     const u64 *rloS = B.rmask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
@@ -221,13 +227,16 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
         }
         const double x0 = pm.x, x1 = pm.y, x2 = pm.z;
         u64 pki = KEY_INF, pkj = KEY_INF;               // correspondence of the previous pass (ring / index parts are the seeds)
+#ifdef ICP_KEEP_SEEDS
+        float4 sv0 = make_float4(0.f, 0.f, 0.f, 0.f), sv1 = sv0; bool sv_ok = false;   // their coordinates, when the previous pass loaded them anyway
+#endif
 
         for (int ps = 0; ps < NP; ps++) {
             const IcpPass &P = s_pass[ps];
             const float thr_f = P.thr_f, thr_excl = P.thr_excl;
             bool kept = false;
             double J[6] = { 0, 0, 0, 0, 0, 0 }, res = 0.0, rho1 = 0.0, rho0h = 0.0;
-            int st_seed = 0, st_exh = 0, st_rings = 0, st_mask = 0;
+            int st_exh = 0, st_rings = 0, st_mask = 0;
             // (all 32 lanes run the pass; lanes without a query are born finished so that the warp votes below stay uniform)
             // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
             double y0, y1, y2;
@@ -253,52 +262,36 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
             const float D = sqrtf(vx * vx + vy * vy), rho = sqrtf(vx * vx + vy * vy + vz * vz);
             const float az = atan2_q(vy, vx), el = atan2_q(vz, D);
-            const int bq = az_bin(az);
 
             u64 ki = KEY_INF, kj = KEY_INF;
             if (active) {
                 // seeds from the previous pass: the two points it chose are real target points => valid bounds
                 if (pki != KEY_INF) {
                     const int s = key_ring(pki), n = key_idx(pki);
-                    const float4 c = __ldg(ptsS + __ldg(rsS + s) + n);
+#ifdef ICP_KEEP_SEEDS
+                    const float4 c = sv_ok ? sv0 : __ldg(ptsS + RS_S(s) + n);
+#else
+                    const float4 c = __ldg(ptsS + RS_S(s) + n);
+#endif
                     const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
                     if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
                 }
                 if (pkj != KEY_INF) {
                     const int s = key_ring(pkj), n = key_idx(pkj);
-                    const float4 c = __ldg(ptsS + __ldg(rsS + s) + n);
+#ifdef ICP_KEEP_SEEDS
+                    const float4 c = sv_ok ? sv1 : __ldg(ptsS + RS_S(s) + n);
+#else
+                    const float4 c = __ldg(ptsS + RS_S(s) + n);
+#endif
                     const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
                     if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
                 }
-                // Phase 1 (probe), only while two rings do not yet hold a candidate: rings in order of increasing elevation
-                // gap (levels of doubling tolerance, read from the ring masks), only the query's own azimuth bin of each.
-#ifndef ICP_PROBE_LEVELS
-#define ICP_PROBE_LEVELS 64        /* levels of doubling elevation tolerance the probe may use (0 = no probe) */
-#endif
-                if (ICP_PROBE_LEVELS > 0 && kj == KEY_INF) {
-                    const float gam_thr = make_window(thr_f, az, D, rho).gam;   // elevation tolerance of the threshold itself
-                    Window ws; ws.full = false; ws.wrapped = false; ws.half = 0.f; ws.b0 = bq; ws.b1 = bq;
-                    u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
-                    int nlev = 0;
-                    for (float lev = 0.0065f; kj == KEY_INF && nlev < ICP_PROBE_LEVELS; lev *= 2.0f, nlev++) {
-                        ws.gam = fminf(lev, gam_thr);
-#pragma unroll
-                        for (int word = 0; word < 4; word++) {
-                            if (word >= W) break;
-                            u64 m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, ws, mask_query(el, ws.gam, rho, 0.f), false) & ~V[word];
-                            V[word] |= m;
-                            while (m && kj == KEY_INF) {
-                                const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1;
-                                merge_key(scan_ring(sorted, csS + s * (VELO_AZ_BINS + 1), s, ws, mx, my, mz, thr_excl, st_seed), ki, kj);
-                            }
-                        }
-                        if (!(lev < gam_thr)) break;
-                    }
-                }
             }
-            // Phase 2 (exhaustive): every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is visited
-            // exactly once, nearest elevation first (levels of doubling tolerance; a single level when the bound is already
-            // tight); the bound, the azimuth window and the elevation tolerance shrink whenever the runner-up improves.
+            // Exhaustive search: every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is visited exactly
+            // once, nearest elevation first (levels of growing tolerance; a single level when the bound is already tight); the bound,
+            // the azimuth window and the elevation tolerance shrink whenever the runner-up improves.  (A separate probe phase that
+            // first looked only at the query's own azimuth bin of the nearest rings, to start with a tight bound, was measured and
+            // removed: without it the unseeded pass evaluates 164 instead of 74 candidates per query and the kernel is 7 % faster.)
             // Written as a warp-synchronous "advance / scan" loop: lanes first advance (cheap ring tests) until each holds a
             // candidate range, then all of them scan together, so the distance loop runs converged.
             float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
@@ -314,14 +307,14 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #else
                 bool started = false, have = false, fin = !active;
 #endif
-                const bool tight = w.gam <= 0.03f;      // seeded / well-probed query: one mask level, window kept for the whole pass
+                const bool tight = w.gam <= ICP_TIGHT;   // seeded query: one mask level, window kept for the whole pass
                 for (;;) {
                     while (!have && !fin) {
                         if (m == 0ull) {                                   // next (level, word)
                             if (started && word + 1 < W) word++;
                             else {
                                 if (started && !(gcur < w.gam)) { fin = true; break; }   // every ring within the tolerance was visited
-                                lev = started ? lev * 2.0f : (tight ? 8.0f : 0.0065f);
+                                lev = started ? lev * ICP_LEVMUL : (tight ? 8.0f : ICP_LEV0);
                                 started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
                             m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, w, mask_query(el, gcur, rho, sqrtf(bound)), true) & ~V[word];
@@ -335,38 +328,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         s_cur = s; have = true; best = scan_init(thr_excl);
                     }
                     if (!__any_sync(FULL, have)) break;
-#ifdef ICP_PAIR
-                    // Lane pairing: a round lasts as long as its longest range, so the lane 16 away (a query 16 points further along the
-                    // ring: a different surface often enough) takes the tail half of the surplus of a longer range, evaluates it against
-                    // the owner's query, and hands the best key back.  The set of evaluated candidates is unchanged: exact.
-                    {
-                        if (have && p0 >= e0) { p0 = p1; e0 = e1; p1 = 0; e1 = 0; }
-                        const bool simple = !have || p1 >= e1;                       // a wrapped window keeps its own work
-                        const int len = (have && simple) ? max(e0 - p0, 0) : 0;
-                        const int olen = __shfl_xor_sync(FULL, len, 16), oe0 = __shfl_xor_sync(FULL, e0, 16);
-                        const float omx = __shfl_xor_sync(FULL, mx, 16), omy = __shfl_xor_sync(FULL, my, 16), omz = __shfl_xor_sync(FULL, mz, 16);
-                        const int osimple = __shfl_xor_sync(FULL, (int)simple, 16);      // (not inside the && below: every lane must take part)
-                        const bool both = simple && osimple != 0;
-                        const int d = len - olen;
-                        const int give = (both && d >= ICP_PAIR) ? (d >> 1) : 0, take = (both && -d >= ICP_PAIR) ? ((-d) >> 1) : 0;
-                        u64 xbest = scan_init(thr_excl);
-                        if (have) {
-                            scan_range(sorted, p0, e0 - give, mx, my, mz, best, st_exh);
-                            p0 = e0;
-                        }
-                        scan_range(sorted, oe0 - take, take > 0 ? oe0 : oe0 - take, omx, omy, omz, xbest, st_exh);
-                        const u64 back = __shfl_xor_sync(FULL, xbest, 16);
-                        if (give > 0) best = min(best, back);
-                        if (have && p1 >= e1) {                              // ring finished
-                            st_rings++; have = false;
-                            if (scan_found(best, thr_excl)) {
-                                const u64 oj = kj;
-                                merge_key(scan_key(best, s_cur), ki, kj);
-                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
-                            }
-                        }
-                    }
-#else
                     if (have) {
                         // at most ICP_SCAN_CHUNK candidates per round: lanes with long ranges continue in the next round while
                         // the others already advance to their next ring, which keeps the distance loop's trip counts uniform
@@ -383,11 +344,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                             }
                         }
                     }
-#endif
                 }
             }
             if (active) {
                 pki = ki; pkj = kj;
+#ifdef ICP_KEEP_SEEDS
+                sv_ok = false;
+#endif
 
                 velo_icp_corr rec;
                 rec.src_ring = sm; rec.src_idx = smi; rec.np_s_i = -1; rec.np_i = 0; rec.np_s_j = -1; rec.np_j = 0; rec.np_k = -1; rec.kept = 0;
@@ -400,13 +363,16 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 if (ki != KEY_INF && kj != KEY_INF) {                        // velo.h:849-851
 #endif
                     const int si = rec.np_s_i, ni = rec.np_i, sj = rec.np_s_j, nj = rec.np_j;
-                    const int ri0 = __ldg(rsS + si), Ln = __ldg(rsS + si + 1) - ri0;
+                    const int ri0 = RS_S(si), Ln = RS_S(si + 1) - ri0;
                     const int k1 = (ni + 1 == Ln) ? 0 : ni + 1, k2 = (ni == 0) ? Ln - 1 : ni - 1;   // (np_i +- 1) mod n, velo.h:852-854
                     const float4 a1 = __ldg(ptsS + ri0 + k1), a2 = __ldg(ptsS + ri0 + k2);
                     const float n1 = d2f(a1.x, a1.y, a1.z, mx, my, mz), n2 = d2f(a2.x, a2.y, a2.z, mx, my, mz);
                     const int nk = (n1 < n2) ? k1 : k2;                      // velo.h:859-863
                     rec.np_k = nk;
-                    const float4 v0 = __ldg(ptsS + ri0 + ni), v1 = __ldg(ptsS + __ldg(rsS + sj) + nj), v2 = (n1 < n2) ? a1 : a2;
+                    const float4 v0 = __ldg(ptsS + ri0 + ni), v1 = __ldg(ptsS + RS_S(sj) + nj), v2 = (n1 < n2) ? a1 : a2;
+#ifdef ICP_KEEP_SEEDS
+                    sv0 = v0; sv1 = v1; sv_ok = true;
+#endif
                     // Eigen::Vector3f (v1-v0).cross(v2-v0), norm(), operator/= (velo.h:868-874)
                     const float ax = __fsub_rn(v1.x, v0.x), ay = __fsub_rn(v1.y, v0.y), az3 = __fsub_rn(v1.z, v0.z);
                     const float bx = __fsub_rn(v2.x, v0.x), by = __fsub_rn(v2.y, v0.y), bz = __fsub_rn(v2.z, v0.z);
@@ -433,11 +399,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
                         const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
                         rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
-#ifdef ICP_LOG_PROD
-                        rho0h = sum;                 // the warp multiplies the 32 arguments and takes ONE logarithm (see the accumulation)
-#else
                         rho0h = 0.5 * U.weight * bb * log(sum);
-#endif
                         rec.kept = 1; rec.residual = res;
                         kept = true;
                     }
@@ -452,7 +414,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #pragma unroll
                     for (int k = 0; k < 6; k++) rec.jacobian[k] = J[k];
 #ifdef VELO_ICP_DEBUG   /* tools/icp_debug_hist.py: per-query search statistics instead of the Jacobian */
-                    rec.jacobian[3] = st_seed; rec.jacobian[4] = st_exh; rec.jacobian[5] = st_rings + 1000.0 * st_mask;
+                    rec.jacobian[3] = 0.0; rec.jacobian[4] = st_exh; rec.jacobian[5] = st_rings + 1000.0 * st_mask;
 #endif
                     corr[(size_t)(corr_stride > 0 ? ps : 0) * corr_stride + q] = rec;
                 }
@@ -478,18 +440,9 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cr0), "+d"(cr1) : "d"(x), "d"(x));
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cw0), "+d"(cw1) : "d"(x), "d"(xw));
                 }
-#ifdef ICP_LOG_PROD
-                // sum of rho/2 = w a^2 / 2 * sum_i log(1 + r_i^2 / a^2) = w a^2 / 2 * log(prod_i (1 + r_i^2 / a^2)); each factor is in
-                // [1, 1 + thr / a^2] (<= 51 for the reference's constants), so the product of 32 cannot overflow
-                double ch = kept ? rho0h : 1.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ch *= __shfl_xor_sync(FULL, ch, o);
-                ch = 0.5 * U.weight * U.loss_a * U.loss_a * log(ch);
-#else
                 double ch = kept ? rho0h : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ch += __shfl_xor_sync(FULL, ch, o);
-#endif
                 // lane holds C[fr][2 fk], C[fr][2 fk + 1]; upper triangle -> record slots (H row-major upper, then g, then cost)
                 double *rec = s_acc[wid][ps];
                 const int c0 = 2 * fk, c1 = c0 + 1;
@@ -503,7 +456,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #endif
             {   // search statistics of the pass: one REDUX per counter, lane 0 adds them to the warp's own counters
                 const unsigned r_kept = __popc(__ballot_sync(FULL, kept));
-                const unsigned r_seed = __reduce_add_sync(FULL, (unsigned)st_seed), r_exh = __reduce_add_sync(FULL, (unsigned)st_exh);
+                const unsigned r_seed = 0u, r_exh = __reduce_add_sync(FULL, (unsigned)st_exh);
                 const unsigned r_rings = __reduce_add_sync(FULL, (unsigned)st_rings), r_mask = __reduce_add_sync(FULL, (unsigned)st_mask);
                 if (lane == 0) {
                     unsigned long long *st = s_stat[wid][ps];
@@ -569,8 +522,11 @@ void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, con
     const int runs_cap = icp_runs_cap(B.N);
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
-    if (corr || frozen) k_icp_pass<true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
-    else k_icp_pass<false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, nullptr, 0, nullptr, 0);
+    const bool rec = corr || frozen, w1 = B.W == 1;
+    if (rec && w1) k_icp_pass<true, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    else if (rec) k_icp_pass<true, false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    else if (w1) k_icp_pass<false, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, nullptr, 0, nullptr, 0);
+    else k_icp_pass<false, false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, nullptr, 0, nullptr, 0);
     if (L.post) L.post(L.user, VK_ICP_PASS);
     dim3 g2(n_units, n_pass);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #endif
     __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
     __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
-    __shared__ unsigned long long s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];   // per warp: no atomics
+    __shared__ unsigned s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];             // per warp and run: no atomics
     __shared__ IcpPass s_pass[VELO_MAX_PASSES];
     __shared__ int s_next;
     if (threadIdx.x == 0) s_next = 0;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #define RS_S(i) __ldg(rsS + (i))
 #endif
     for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 56; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
-    for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0][0])[i] = 0ull;
+    for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0][0])[i] = 0u;
     if (tid == 0) {
         int q = 0;
         for (int s = 0; s < nrM; s++) { s_q[s] = q; int r0 = rsM[s], L = rsM[s + 1] - r0; s_rsM[s] = r0; q += (L + skip - 1) / skip; }
@@ -239,24 +239,29 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             int st_exh = 0, st_rings = 0, st_mask = 0;
             // (all 32 lanes run the pass; lanes without a query are born finished so that the warp votes below stay uniform)
             // util::transform_point (utility.h:97-103) = ceres::AngleAxisRotatePoint in f64, op for op (hazard H8)
-            double y0, y1, y2;
-            if (!P.pose.small_angle) {
-                const double c0 = __dsub_rn(__dmul_rn(P.pose.u[1], x2), __dmul_rn(P.pose.u[2], x1));
-                const double c1 = __dsub_rn(__dmul_rn(P.pose.u[2], x0), __dmul_rn(P.pose.u[0], x2));
-                const double c2 = __dsub_rn(__dmul_rn(P.pose.u[0], x1), __dmul_rn(P.pose.u[1], x0));
-                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.pose.u[0], x0), __dmul_rn(P.pose.u[1], x1)), __dmul_rn(P.pose.u[2], x2));
-                const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.pose.c));
-                y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.pose.c), __dmul_rn(c0, P.pose.s)), __dmul_rn(P.pose.u[0], tmp));
-                y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.pose.c), __dmul_rn(c1, P.pose.s)), __dmul_rn(P.pose.u[1], tmp));
-                y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.pose.c), __dmul_rn(c2, P.pose.s)), __dmul_rn(P.pose.u[2], tmp));
-            } else {
-                y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.pose.w[1], x2), __dmul_rn(P.pose.w[2], x1)));
-                y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.pose.w[2], x0), __dmul_rn(P.pose.w[0], x2)));
-                y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.pose.w[0], x1), __dmul_rn(P.pose.w[1], x0)));
+#define ICP_ROTATE(y0, y1, y2) \
+            if (!P.pose.small_angle) { \
+                const double c0 = __dsub_rn(__dmul_rn(P.pose.u[1], x2), __dmul_rn(P.pose.u[2], x1)); \
+                const double c1 = __dsub_rn(__dmul_rn(P.pose.u[2], x0), __dmul_rn(P.pose.u[0], x2)); \
+                const double c2 = __dsub_rn(__dmul_rn(P.pose.u[0], x1), __dmul_rn(P.pose.u[1], x0)); \
+                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(P.pose.u[0], x0), __dmul_rn(P.pose.u[1], x1)), __dmul_rn(P.pose.u[2], x2)); \
+                const double tmp = __dmul_rn(dot, __dsub_rn(1.0, P.pose.c)); \
+                y0 = __dadd_rn(__dadd_rn(__dmul_rn(x0, P.pose.c), __dmul_rn(c0, P.pose.s)), __dmul_rn(P.pose.u[0], tmp)); \
+                y1 = __dadd_rn(__dadd_rn(__dmul_rn(x1, P.pose.c), __dmul_rn(c1, P.pose.s)), __dmul_rn(P.pose.u[1], tmp)); \
+                y2 = __dadd_rn(__dadd_rn(__dmul_rn(x2, P.pose.c), __dmul_rn(c2, P.pose.s)), __dmul_rn(P.pose.u[2], tmp)); \
+            } else { \
+                y0 = __dadd_rn(x0, __dsub_rn(__dmul_rn(P.pose.w[1], x2), __dmul_rn(P.pose.w[2], x1))); \
+                y1 = __dadd_rn(x1, __dsub_rn(__dmul_rn(P.pose.w[2], x0), __dmul_rn(P.pose.w[0], x2))); \
+                y2 = __dadd_rn(x2, __dsub_rn(__dmul_rn(P.pose.w[0], x1), __dmul_rn(P.pose.w[1], x0))); \
             }
-            const float mx = __double2float_rn(__dadd_rn(y0, P.pose.t[0]));
-            const float my = __double2float_rn(__dadd_rn(y1, P.pose.t[1]));
-            const float mz = __double2float_rn(__dadd_rn(y2, P.pose.t[2]));
+            float mx, my, mz;
+            {
+                double y0, y1, y2;
+                ICP_ROTATE(y0, y1, y2)
+                mx = __double2float_rn(__dadd_rn(y0, P.pose.t[0]));
+                my = __double2float_rn(__dadd_rn(y1, P.pose.t[1]));
+                mz = __double2float_rn(__dadd_rn(y2, P.pose.t[2]));
+            }
 
             // ---- pruning geometry of the query in the index frame of the target scan
             float vx, vy, vz; idx_frame(cal, mx, my, mz, vx, vy, vz);
@@ -387,6 +392,9 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         rec.normal[0] = nx; rec.normal[1] = ny; rec.normal[2] = nz;
                         // cost3DPD (costfunctions.h:40-53): M = R p; M += t - o; r = M . n
                         const double dnx = nx, dny = ny, dnz = nz;
+                        // (the rotated point is formed again here rather than kept in six registers across the whole search)
+                        double y0, y1, y2;
+                        ICP_ROTATE(y0, y1, y2)
                         const double m0 = y0 + (P.pose.t[0] - (double)v0.x), m1 = y1 + (P.pose.t[1] - (double)v0.y), m2 = y2 + (P.pose.t[2] - (double)v0.z);
                         res = m0 * dnx + m1 * dny + m2 * dnz;
 #pragma unroll
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 const unsigned r_seed = 0u, r_exh = __reduce_add_sync(FULL, (unsigned)st_exh);
                 const unsigned r_rings = __reduce_add_sync(FULL, (unsigned)st_rings), r_mask = __reduce_add_sync(FULL, (unsigned)st_mask);
                 if (lane == 0) {
-                    unsigned long long *st = s_stat[wid][ps];
+                    unsigned *st = s_stat[wid][ps];
                     st[0] += r_kept; st[1] += r_seed; st[2] += r_exh; st[3] += r_rings; st[4] += r_mask;
                 }
             }
@@ -478,7 +486,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 po[i] = v;
             }
             __syncwarp();
-            for (int i = lane; i < NP * 5; i += 32) (&s_stat[wid][0][0])[i] = 0ull;
+            for (int i = lane; i < NP * 5; i += 32) (&s_stat[wid][0][0])[i] = 0u;
             __syncwarp();
         }
     }

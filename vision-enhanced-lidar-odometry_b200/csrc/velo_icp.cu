@@ -31,10 +31,13 @@
 #define ICP_TIGHT 0.03f        /* elevation tolerance (rad) up to which a query's ring set is taken in one mask level */
 #endif
 #ifndef ICP_LEV0
-#define ICP_LEV0 0.0065f       /* first elevation-tolerance level of a query that is not tight (about one ring spacing) */
+#define ICP_LEV0 0.013f        /* first elevation-tolerance level of a query that is not tight (about two ring spacings; 0.0065 measured 1 % slower) */
+#endif
+#ifndef ICP_OPT_FRAC
+#define ICP_OPT_FRAC 0.25f     /* optimistic squared search radius of an unseeded query, as a fraction of the threshold (0 = off) */
 #endif
 #ifndef ICP_LEVMUL
-#define ICP_LEVMUL 2.0f        /* growth of the tolerance from level to level */
+#define ICP_LEVMUL 4.0f        /* growth of the tolerance from level to level (2.0 measured 1 % slower) */
 #endif
 #define VELO_STR_(x) #x
 #define VELO_UNROLL(n) _Pragma(VELO_STR_(unroll n))
@@ -156,9 +159,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                                                           IcpFrozen *__restrict__ frozen, int frozen_stride) {
     __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
     __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
-#ifdef ICP_RS_SMEM
-    __shared__ int s_rsS[VELO_MAX_RINGS_HARD + 1];
-#endif
+    __shared__ int s_rsS[VELO_MAX_RINGS_HARD + 1];    // ring starts of the target scan (seeds and the third point read them every pass)
     __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
     __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
     __shared__ unsigned s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];             // per warp and run: no atomics
@@ -175,12 +176,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const int skip = U.skip;
     for (int i = tid; i < (int)(NP * sizeof(IcpPass) / sizeof(double)); i += blockDim.x)
         reinterpret_cast<double *>(s_pass)[i] = reinterpret_cast<const double *>(U.pass)[i];
-#ifdef ICP_RS_SMEM
     for (int i = tid; i <= B.n_rings[U.tgt_slot]; i += blockDim.x) s_rsS[i] = rsS[i];
 #define RS_S(i) s_rsS[i]
-#else
-#define RS_S(i) __ldg(rsS + (i))
-#endif
     for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 56; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
     for (int i = tid; i < (ICP_THREADS / 32) * VELO_MAX_PASSES * 5; i += blockDim.x) (&s_stat[0][0][0])[i] = 0u;
     if (tid == 0) {
@@ -227,9 +224,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
         }
         const double x0 = pm.x, x1 = pm.y, x2 = pm.z;
         u64 pki = KEY_INF, pkj = KEY_INF;               // correspondence of the previous pass (ring / index parts are the seeds)
-#ifdef ICP_KEEP_SEEDS
-        float4 sv0 = make_float4(0.f, 0.f, 0.f, 0.f), sv1 = sv0; bool sv_ok = false;   // their coordinates, when the previous pass loaded them anyway
-#endif
 
         for (int ps = 0; ps < NP; ps++) {
             const IcpPass &P = s_pass[ps];
@@ -273,21 +267,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 // seeds from the previous pass: the two points it chose are real target points => valid bounds
                 if (pki != KEY_INF) {
                     const int s = key_ring(pki), n = key_idx(pki);
-#ifdef ICP_KEEP_SEEDS
-                    const float4 c = sv_ok ? sv0 : __ldg(ptsS + RS_S(s) + n);
-#else
                     const float4 c = __ldg(ptsS + RS_S(s) + n);
-#endif
                     const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
                     if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
                 }
                 if (pkj != KEY_INF) {
                     const int s = key_ring(pkj), n = key_idx(pkj);
-#ifdef ICP_KEEP_SEEDS
-                    const float4 c = sv_ok ? sv1 : __ldg(ptsS + RS_S(s) + n);
-#else
                     const float4 c = __ldg(ptsS + RS_S(s) + n);
-#endif
                     const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
                     if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
                 }
@@ -299,7 +285,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             // removed: without it the unseeded pass evaluates 164 instead of 74 candidates per query and the kernel is 7 % faster.)
             // Written as a warp-synchronous "advance / scan" loop: lanes first advance (cheap ring tests) until each holds a
             // candidate range, then all of them scan together, so the distance loop runs converged.
-            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+            // A query without seeds (first pass) starts OPTIMISTICALLY: the search is made exhaustive only for the squared radius
+            // cap = ICP_OPT_FRAC * threshold.  If two rings hold a point within cap, the result is already exact (anything outside
+            // is farther than both); otherwise the lane escalates to the full threshold and walks again.  Most queries have their two
+            // rings well inside a quarter of the threshold, and windows and ring sets scale with the radius.
+            float cap = thr_f;
+            if (ICP_OPT_FRAC > 0.f && pki == KEY_INF && pkj == KEY_INF) cap = thr_f * ICP_OPT_FRAC;
+            float bound = (kj == KEY_INF) ? cap : fminf(cap, key_d2(kj));
             Window w = make_window(bound, az, D, rho);
             {
                 u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
@@ -312,13 +304,21 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #else
                 bool started = false, have = false, fin = !active;
 #endif
-                const bool tight = w.gam <= ICP_TIGHT;   // seeded query: one mask level, window kept for the whole pass
+                bool tight = w.gam <= ICP_TIGHT;         // seeded query: one mask level, window kept for the whole pass
                 for (;;) {
                     while (!have && !fin) {
                         if (m == 0ull) {                                   // next (level, word)
                             if (started && word + 1 < W) word++;
                             else {
-                                if (started && !(gcur < w.gam)) { fin = true; break; }   // every ring within the tolerance was visited
+                                if (started && !(gcur < w.gam)) {                        // every ring within the tolerance was visited
+                                    if (cap < thr_f && (kj == KEY_INF || key_d2(kj) > cap)) {   // not certified inside the optimistic radius
+                                        cap = thr_f; bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+                                        w = make_window(bound, az, D, rho); tight = w.gam <= ICP_TIGHT;
+                                        started = false; V[0] = V[1] = V[2] = V[3] = 0ull;
+                                        continue;
+                                    }
+                                    fin = true; break;
+                                }
                                 lev = started ? lev * ICP_LEVMUL : (tight ? 8.0f : ICP_LEV0);
                                 started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                             if (scan_found(best, thr_excl)) {
                                 const u64 oj = kj;
                                 merge_key(scan_key(best, s_cur), ki, kj);
-                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
+                                if (kj != oj) { bound = fminf(cap, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
                             }
                         }
                     }
@@ -353,9 +353,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             }
             if (active) {
                 pki = ki; pkj = kj;
-#ifdef ICP_KEEP_SEEDS
-                sv_ok = false;
-#endif
 
                 velo_icp_corr rec;
                 rec.src_ring = sm; rec.src_idx = smi; rec.np_s_i = -1; rec.np_i = 0; rec.np_s_j = -1; rec.np_j = 0; rec.np_k = -1; rec.kept = 0;
@@ -375,9 +372,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     const int nk = (n1 < n2) ? k1 : k2;                      // velo.h:859-863
                     rec.np_k = nk;
                     const float4 v0 = __ldg(ptsS + ri0 + ni), v1 = __ldg(ptsS + RS_S(sj) + nj), v2 = (n1 < n2) ? a1 : a2;
-#ifdef ICP_KEEP_SEEDS
-                    sv0 = v0; sv1 = v1; sv_ok = true;
-#endif
                     // Eigen::Vector3f (v1-v0).cross(v2-v0), norm(), operator/= (velo.h:868-874)
                     const float ax = __fsub_rn(v1.x, v0.x), ay = __fsub_rn(v1.y, v0.y), az3 = __fsub_rn(v1.z, v0.z);
                     const float bx = __fsub_rn(v2.x, v0.x), by = __fsub_rn(v2.y, v0.y), bz = __fsub_rn(v2.z, v0.z);

@@ -33,9 +33,6 @@
 #ifndef ICP_LEV0
 #define ICP_LEV0 0.013f        /* first elevation-tolerance level of a query that is not tight (about two ring spacings; 0.0065 measured 1 % slower) */
 #endif
-#ifndef ICP_OPT_FRAC
-#define ICP_OPT_FRAC 0.25f     /* optimistic squared search radius of an unseeded query, as a fraction of the threshold (0 = off) */
-#endif
 #ifndef ICP_LEVMUL
 #define ICP_LEVMUL 4.0f        /* growth of the tolerance from level to level (2.0 measured 1 % slower) */
 #endif
@@ -285,14 +282,14 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             // removed: without it the unseeded pass evaluates 164 instead of 74 candidates per query and the kernel is 7 % faster.)
             // Written as a warp-synchronous "advance / scan" loop: lanes first advance (cheap ring tests) until each holds a
             // candidate range, then all of them scan together, so the distance loop runs converged.
-            // A query without seeds (first pass) starts OPTIMISTICALLY: the search is made exhaustive only for the squared radius
-            // cap = ICP_OPT_FRAC * threshold.  If two rings hold a point within cap, the result is already exact (anything outside
-            // is farther than both); otherwise the lane escalates to the full threshold and walks again.  Most queries have their two
-            // rings well inside a quarter of the threshold, and windows and ring sets scale with the radius.
-            float cap = thr_f;
-            if (ICP_OPT_FRAC > 0.f && pki == KEY_INF && pkj == KEY_INF) cap = thr_f * ICP_OPT_FRAC;
-            float bound = (kj == KEY_INF) ? cap : fminf(cap, key_d2(kj));
+            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
             Window w = make_window(bound, az, D, rho);
+#ifdef ICP_WIN_I
+            // the ring of seed i only has to yield its own nearest point, which is at most as far as the seed: a window sized by d_i
+            const int s_i = (ki != KEY_INF) ? key_ring(ki) : -1;
+            Window wi = w;
+            if (ki != KEY_INF) wi = make_window(key_d2(ki), az, D, rho);
+#endif
             {
                 u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
                 u64 m = 0ull;
@@ -304,21 +301,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
 #else
                 bool started = false, have = false, fin = !active;
 #endif
-                bool tight = w.gam <= ICP_TIGHT;         // seeded query: one mask level, window kept for the whole pass
+                const bool tight = w.gam <= ICP_TIGHT;   // seeded query: one mask level, window kept for the whole pass
                 for (;;) {
                     while (!have && !fin) {
                         if (m == 0ull) {                                   // next (level, word)
                             if (started && word + 1 < W) word++;
                             else {
-                                if (started && !(gcur < w.gam)) {                        // every ring within the tolerance was visited
-                                    if (cap < thr_f && (kj == KEY_INF || key_d2(kj) > cap)) {   // not certified inside the optimistic radius
-                                        cap = thr_f; bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
-                                        w = make_window(bound, az, D, rho); tight = w.gam <= ICP_TIGHT;
-                                        started = false; V[0] = V[1] = V[2] = V[3] = 0ull;
-                                        continue;
-                                    }
-                                    fin = true; break;
-                                }
+                                if (started && !(gcur < w.gam)) { fin = true; break; }   // every ring within the tolerance was visited
                                 lev = started ? lev * ICP_LEVMUL : (tight ? 8.0f : ICP_LEV0);
                                 started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
@@ -328,8 +317,16 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         }
                         const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
                         const int *cs = csS + s * (VELO_AZ_BINS + 1);
+#ifdef ICP_WIN_I
+                        const bool own = s == s_i;
+                        const int wb0 = own ? wi.b0 : w.b0, wb1 = own ? wi.b1 : w.b1;
+                        const bool wwr = own ? wi.wrapped : w.wrapped;
+                        if (!wwr) { p0 = __ldg(cs + wb0); e0 = __ldg(cs + wb1 + 1); p1 = 0; e1 = 0; }
+                        else { p0 = __ldg(cs + wb0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + wb1 + 1); }
+#else
                         if (!w.wrapped) { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + w.b1 + 1); p1 = 0; e1 = 0; }
                         else { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + w.b1 + 1); }
+#endif
                         s_cur = s; have = true; best = scan_init(thr_excl);
                     }
                     if (!__any_sync(FULL, have)) break;
@@ -345,7 +342,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                             if (scan_found(best, thr_excl)) {
                                 const u64 oj = kj;
                                 merge_key(scan_key(best, s_cur), ki, kj);
-                                if (kj != oj) { bound = fminf(cap, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
+                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
                             }
                         }
                     }
@@ -399,7 +396,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         }
                         J[3] = dnx; J[4] = dny; J[5] = dnz;
                         // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
+                        #ifdef ICP_FAST_RCP
+                        const double bb = U.loss_a * U.loss_a, cc = __drcp_rn(bb), sum = 1.0 + res * res * cc, inv = __drcp_rn(sum);   // correctly rounded 1/x == 1.0 / x
+#else
                         const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
+#endif
                         rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
                         rho0h = 0.5 * U.weight * bb * log(sum);
                         rec.kept = 1; rec.residual = res;

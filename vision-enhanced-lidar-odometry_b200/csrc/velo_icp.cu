@@ -284,12 +284,6 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             // candidate range, then all of them scan together, so the distance loop runs converged.
             float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
             Window w = make_window(bound, az, D, rho);
-#ifdef ICP_WIN_I
-            // the ring of seed i only has to yield its own nearest point, which is at most as far as the seed: a window sized by d_i
-            const int s_i = (ki != KEY_INF) ? key_ring(ki) : -1;
-            Window wi = w;
-            if (ki != KEY_INF) wi = make_window(key_d2(ki), az, D, rho);
-#endif
             {
                 u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
                 u64 m = 0ull;
@@ -317,16 +311,8 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         }
                         const int s = word * 64 + __ffsll((long long)m) - 1; m &= m - 1; st_mask++;
                         const int *cs = csS + s * (VELO_AZ_BINS + 1);
-#ifdef ICP_WIN_I
-                        const bool own = s == s_i;
-                        const int wb0 = own ? wi.b0 : w.b0, wb1 = own ? wi.b1 : w.b1;
-                        const bool wwr = own ? wi.wrapped : w.wrapped;
-                        if (!wwr) { p0 = __ldg(cs + wb0); e0 = __ldg(cs + wb1 + 1); p1 = 0; e1 = 0; }
-                        else { p0 = __ldg(cs + wb0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + wb1 + 1); }
-#else
                         if (!w.wrapped) { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + w.b1 + 1); p1 = 0; e1 = 0; }
                         else { p0 = __ldg(cs + w.b0); e0 = __ldg(cs + VELO_AZ_BINS); p1 = __ldg(cs); e1 = __ldg(cs + w.b1 + 1); }
-#endif
                         s_cur = s; have = true; best = scan_init(thr_excl);
                     }
                     if (!__any_sync(FULL, have)) break;
@@ -396,11 +382,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         }
                         J[3] = dnx; J[4] = dny; J[5] = dnz;
                         // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
-                        #ifdef ICP_FAST_RCP
-                        const double bb = U.loss_a * U.loss_a, cc = __drcp_rn(bb), sum = 1.0 + res * res * cc, inv = __drcp_rn(sum);   // correctly rounded 1/x == 1.0 / x
-#else
-                        const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
-#endif
+                                                const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
                         rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
                         rho0h = 0.5 * U.weight * bb * log(sum);
                         rec.kept = 1; rec.residual = res;

@@ -132,14 +132,24 @@ __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal,
                 atomicAdd(&s_hist[b], 1);
             }
             if (i0 == 0) bins[k] = b;
-            // sector bounds: lanes of a warp hold consecutive points, i.e. mostly one sector -> reduce inside the warp first
-            const unsigned act = __ballot_sync(FULL, i < L);
-            if (i < L) {
-                const int sec = b / VELO_BINS_PER_SECTOR;
-                const unsigned grp = __match_any_sync(act, sec);
-                const int elo = __reduce_min_sync(grp, e), ehi = __reduce_max_sync(grp, e), rlo = __reduce_min_sync(grp, rr), rhi = __reduce_max_sync(grp, rr);
-                if ((int)(__ffs(grp) - 1) == (tid & 31)) {
-                    atomicMin(&s_lo[sec], elo); atomicMax(&s_hi[sec], ehi); atomicMin(&s_rlo[sec], rlo); atomicMax(&s_rhi[sec], rhi);
+            // sector bounds: the 32 lanes hold consecutive points of the ring, i.e. one sector or two neighbouring ones.  Each of the
+            // (at most two) sectors present at the ends of the warp is reduced with full-mask REDUX (lanes outside contribute the
+            // neutral element) and written by one lane; a lane in neither (noise in the point order) writes for itself.
+            {
+                const int sec = (i < L) ? b / VELO_BINS_PER_SECTOR : -1;
+                const unsigned act = __ballot_sync(FULL, i < L);
+                if (act) {
+                    const int secA = __shfl_sync(FULL, sec, __ffs(act) - 1), secB = __shfl_sync(FULL, sec, 31 - __clz(act));
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        const int sg = g == 0 ? secA : secB;
+                        if (g == 1 && secB == secA) break;
+                        const bool mine = sec == sg;
+                        const int elo = __reduce_min_sync(FULL, mine ? e : 0x7fffffff), ehi = __reduce_max_sync(FULL, mine ? e : (int)0x80000000);
+                        const int rlo = __reduce_min_sync(FULL, mine ? rr : 0x7fffffff), rhi = __reduce_max_sync(FULL, mine ? rr : (int)0x80000000);
+                        if ((tid & 31) == 0) { atomicMin(&s_lo[sg], elo); atomicMax(&s_hi[sg], ehi); atomicMin(&s_rlo[sg], rlo); atomicMax(&s_rhi[sg], rhi); }
+                    }
+                    if (i < L && sec != secA && sec != secB) { atomicMin(&s_lo[sec], e); atomicMax(&s_hi[sec], e); atomicMin(&s_rlo[sec], rr); atomicMax(&s_rhi[sec], rr); }
                 }
             }
         }
@@ -458,36 +468,42 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // x tables: lut[s][b] = first index of ring s whose bucket is >= b (points are bucket-sorted on a ring with non-decreasing x);
-        // a decreasing x marks the ring for the exact search.  Zone ranges: warp-reduced per zone before they go to shared memory.
+        // a decreasing x marks the ring for the exact search.
         for (int s = wid; s < nr; s += nwarps) {
             const float2 *ps = s_proj + s_off[s];
             unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
             const int cnt = s_cnt[s];
+            float xprev = 0.f; int bprev = -1;                               // last point of the previous 32 (lane 31's)
             for (int i0 = 0; i0 <= cnt; i0 += 32) {
                 const int i = i0 + lane;
                 const bool in = i < cnt;
-                const float2 pi = in ? ps[i] : make_float2(0.f, 0.f);
+                const float xi = in ? ps[i].x : 0.f;
+                const int bi = in ? assoc_xbucket(xi, xmin, xscale) : ASSOC_NB;
+                float xp = __shfl_up_sync(FULL, xi, 1); int bp = __shfl_up_sync(FULL, bi, 1);
+                if (lane == 0) { xp = xprev; bp = bprev; }
                 if (i <= cnt) {
-                    const float xp = i > 0 ? ps[i - 1].x : 0.f;
-                    const int bp = i > 0 ? assoc_xbucket(xp, xmin, xscale) : -1, bi = in ? assoc_xbucket(pi.x, xmin, xscale) : ASSOC_NB;
-                    if (i > 0 && in && xp > pi.x) s_mono[s] = 0;
+                    if (i > 0 && in && xp > xi) s_mono[s] = 0;
                     for (int b = bp + 1; b <= bi; b++) lut[b] = (unsigned short)i;
                 }
-                if (use2d) {
-                    // a point counts for every zone a keypoint within the width gate of it can fall in (1 or 2 zones)
-                    const int z0 = assoc_zone(pi.x - zpad, xmin, zscale), z1 = assoc_zone(pi.x + zpad, xmin, zscale), yo = f2ord(pi.y);
-                    const unsigned act = __ballot_sync(FULL, in);
-                    if (in) {
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const int z = k == 0 ? z0 : z1;
-                            const unsigned grp = __match_any_sync(act, z);
-                            const int lo = __reduce_min_sync(grp, yo), hi = __reduce_max_sync(grp, yo);
-                            if ((int)(__ffs(grp) - 1) == lane && (k == 0 || z1 != z0)) { atomicMin(&s_zr[s][z].x, lo); atomicMax(&s_zr[s][z].y, hi); }
-                        }
-                        for (int z = z0 + 1; z < z1; z++) { atomicMin(&s_zr[s][z].x, yo); atomicMax(&s_zr[s][z].y, yo); }   // (zones narrower than the gate: never with 16 zones)
-                    }
-                }
+                xprev = __shfl_sync(FULL, xi, 31); bprev = __shfl_sync(FULL, bi, 31);
+            }
+        }
+        __syncthreads();
+        // zone ranges: one thread per (ring, zone).  On a ring with non-decreasing x the points whose x lies in the zone widened by
+        // the width gate are one index span, read off the x table (buckets are monotone in x, so the span of the buckets that
+        // the widened zone touches covers them); any other ring counts with its whole y range.
+        if (use2d) {
+            for (int t = tid; t < nr * ASSOC_ZONES; t += blockDim.x) {
+                const int s = t / ASSOC_ZONES, z = t % ASSOC_ZONES;
+                float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+                if (s_mono[s]) {
+                    const float zlo = xmin + z / zscale - zpad, zhi = xmin + (z + 1) / zscale + zpad;
+                    const unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
+                    const float2 *ps = s_proj + s_off[s];
+                    const int i0 = z == 0 ? 0 : lut[assoc_xbucket(zlo, xmin, xscale)], i1 = z == ASSOC_ZONES - 1 ? s_cnt[s] : lut[assoc_xbucket(zhi, xmin, xscale) + 1];
+                    for (int i = i0; i < i1; i++) { const float y = ps[i].y; lo = fminf(lo, y); hi = fmaxf(hi, y); }
+                } else { lo = s_yr[s].x; hi = s_yr[s].y; }
+                s_zr[s][z] = make_int2(f2ord(lo), f2ord(hi));
             }
         }
     }

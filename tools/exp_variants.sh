@@ -2,7 +2,7 @@
 # build variants of libvelo_gpu.so on the GPU box (EXPS: ';'-separated nvcc flag sets) and bench each briefly; the default build is restored last
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-IFS=';' read -ra LIST <<< "${EXPS:-;-DICP_LEGACY}"
+IFS=";" read -ra LIST <<< "${EXPS-;}"
 for ex in "${LIST[@]}" ""; do
   VELO_NVCC_EXTRA="$ex" python -c "
 import importlib; b=importlib.import_module('vision-enhanced-lidar-odometry_b200._build'); b.build_gpu(force=True)" 2>&1 | grep -iE " error|ptxas fatal"

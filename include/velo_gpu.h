@@ -299,9 +299,10 @@ int  velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int
 int  velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *icp_neq, double *vis_neq,
                              int *has_depth, int *n_hits);
 /* the whole front end for a batch in one call: upload (pinned host buffers) -> all stages -> download, with the upload of
- * chunk c+1 overlapping the kernels of chunk c on a second stream (chunk = frames per chunk; 0 = a small first chunk, then
- * doubling up to count/4: only the first upload is exposed and few launches end with a tail).  Slot slot0 is
- * the halo scan when slot0 == 0 (no frame pair for it).  Synchronises. */
+ * chunk c+1 overlapping the kernels of chunk c on a second stream (chunk = frames per chunk; 0 = a small first chunk — the only
+ * upload nothing can hide — then geometric growth up to count/8, the factor (1.15 .. 2) adapted from the previous call so that a
+ * chunk never takes longer to arrive than its predecessor takes to compute).  Slot slot0 is the halo scan when slot0 == 0 (no
+ * frame pair for it).  Results do not depend on the chunking.  Synchronises. */
 int  velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
                              double *icp_neq, double *vis_neq, int *has_depth, int *n_hits);
 /* number of kernel launches issued by this context since creation */

@@ -19,6 +19,8 @@ struct velo_gpu_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;   // stream2: every other chunk of batch_frontend
     cudaStream_t launch_stream = nullptr;                                        // stream of the launch being profiled
     std::vector<cudaEvent_t> chunk_ev;
+    cudaEvent_t fe_up0 = nullptr, fe_up1 = nullptr, fe_c0 = nullptr, fe_c1 = nullptr;   // batch_frontend: upload / whole-call timing of the last call
+    float fe_growth = 2.0f;                                                             // chunk growth factor derived from it
     velo_gpu_params prm;
     velo_gpu_calib cal;
     DevCalib dcal;
@@ -364,6 +366,7 @@ extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : { ctx->fe_up0, ctx->fe_up1, ctx->fe_c0, ctx->fe_c1 }) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1176,20 +1179,29 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
     if (!ctx || !in) return VELO_ERR_INVALID_ARG;
     if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
-    // chunk boundaries: a fixed size if the caller gives one; otherwise a small first chunk (the only upload nothing can hide)
-    // doubling up to count/4, because every chunk ends with the tail of its own correspondence launch
+    // chunk boundaries: a fixed size if the caller gives one; otherwise a small first chunk (the only upload nothing can hide) growing
+    // geometrically up to count/8.  A chunk's kernels can only start when ALL of it has arrived, so a chunk must not take longer to
+    // upload than its predecessor takes to compute: the growth factor is 0.9 x (time of the previous call / time of its uploads),
+    // clamped to [1.15, 2] — 2 when the copies are fast (one GPU alone on the host: 55 GB/s), ~1.2 when eight GPUs share it (23 GB/s).
     std::vector<int> cut(1, 0);
     if (chunk > 0) { for (int i = chunk; i < count; i += chunk) cut.push_back(i); }
-    else { const int cap = std::max(32, count / 4); for (int i = std::max(16, count / 64), n = i; i < count; n = std::min(2 * n, cap), i += n) cut.push_back(i); }
-    if (chunk <= 0 && cut.size() > 1 && count - cut.back() < 32) cut.pop_back();      // no tiny last chunk
+    else {
+        const int cap = std::max(32, count / 8);
+        double n = std::max(16, count / 64);
+        for (int i = (int)n; i < count; n = std::min(n * ctx->fe_growth, (double)cap), i += (int)n) cut.push_back(i);
+    }
+    if (chunk <= 0 && cut.size() > 1 && count - cut.back() < 16) cut.pop_back();      // no tiny last chunk
     cut.push_back(count);
     const int nchunks = (int)cut.size() - 1;
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while ((int)ctx->chunk_ev.size() < nchunks + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    if (!ctx->fe_up0) { CK(cudaEventCreate(&ctx->fe_up0)); CK(cudaEventCreate(&ctx->fe_up1)); CK(cudaEventCreate(&ctx->fe_c0)); CK(cudaEventCreate(&ctx->fe_c1)); }
+    CK(cudaEventRecord(ctx->fe_c0, ctx->stream));
     // the copy stream must not overwrite slots that earlier work on the compute stream may still read
     CK(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[nchunks], 0));
+    CK(cudaEventRecord(ctx->fe_up0, ctx->copy_stream));
     // chunks alternate between two compute streams, so the tail of one chunk's correspondence launch overlaps the next chunk's
     // kernels; a chunk's frame pairs read the previous chunk's last scan, hence the wait on its index / projection stages
     // (per-kernel profiling needs serial launches: one stream then)
@@ -1215,9 +1227,17 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
         rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], VELO_STAGE_ICP | VELO_STAGE_VISUAL, 1);
         if (rc) return rc;
     }
+    CK(cudaEventRecord(ctx->fe_up1, ctx->copy_stream));
     if (two) { CK(cudaEventRecord(ev_light[nchunks], ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ev_light[nchunks], 0)); }
     ctx->launch_stream = ctx->stream;
-    return velo_gpu_batch_download(ctx, slot0, count, icp_neq, vis_neq, has_depth, n_hits);
+    const int rc = velo_gpu_batch_download(ctx, slot0, count, icp_neq, vis_neq, has_depth, n_hits);
+    if (rc == VELO_OK && chunk <= 0) {        // how fast the copies were against the whole call: the next call's chunk growth
+        CK(cudaEventRecord(ctx->fe_c1, ctx->stream)); CK(cudaEventSynchronize(ctx->fe_c1)); CK(cudaEventSynchronize(ctx->fe_up1));
+        float up = 0.f, all = 0.f;
+        CK(cudaEventElapsedTime(&up, ctx->fe_up0, ctx->fe_up1)); CK(cudaEventElapsedTime(&all, ctx->fe_c0, ctx->fe_c1));
+        if (up > 0.f && all > 0.f) ctx->fe_growth = std::min(2.0f, std::max(1.15f, 0.9f * all / up));
+    }
+    return rc;
 }
 
 extern "C" int velo_gpu_batch_counts(velo_gpu_ctx *ctx, int slot0, int count, int *n_points, int *n_rings, int *proj_total, int *status) {

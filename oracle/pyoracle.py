@@ -31,9 +31,16 @@ def build_oracle(force=False):
         return ORACLE_LIB
     if shutil.which("g++") is None and os.path.isfile(ORACLE_LIB):
         return ORACLE_LIB
-    # no -march, no FMA contraction: mirrors the reference build (CMakeLists.txt:30)
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w",
-                    "-o", ORACLE_LIB, src], check=True)
+    # no -march, no FMA contraction: mirrors the reference build (CMakeLists.txt:30).  Built under a lock into a temporary name
+    # (several test / bench processes may start at once).
+    import fcntl
+    with open(ORACLE_LIB + ".lock", "w") as lf:
+        fcntl.flock(lf, fcntl.LOCK_EX)
+        fresh = os.path.isfile(ORACLE_LIB) and all(os.path.getmtime(ORACLE_LIB) >= os.path.getmtime(s) for s in (src, hdr))
+        if not fresh or force:
+            tmp = f"{ORACLE_LIB}.tmp.{os.getpid()}"
+            subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-o", tmp, src], check=True)
+            os.replace(tmp, ORACLE_LIB)
     return ORACLE_LIB
 
 

@@ -134,3 +134,26 @@ def test_no_fused_packed_f32_in_product_sass():
     sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
     assert "FMUL2" in sass and "FADD2" in sass          # the packed path is really there
     assert "FFMA2" not in sass
+
+
+def test_concurrent_builds_do_not_corrupt_the_library(velo):
+    """eight ranks of one torchrun import the package at once: a (re)build must be serialised and published atomically (a stale
+    header once made all ranks rebuild libvelo_gpu.so into the same file: "file too short")"""
+    import subprocess
+    import sys
+    code = ("import importlib, ctypes; b = importlib.import_module('vision-enhanced-lidar-odometry_b200._build'); "
+            "p = b.build_synth(force=True); ctypes.CDLL(p).velo_synth_calib")
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=ROOT, stderr=subprocess.PIPE) for _ in range(6)]
+    for p in procs:
+        _, err = p.communicate(timeout=120)
+        assert p.returncode == 0, err.decode()[-500:]
+
+
+def test_pose_vec2mat_is_rodrigues(velo):
+    """util::pose_mat2vec (utility.h:67-82): AngleAxisToRotationMatrix + translation, incl. the first-order branch near zero"""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(4)
+    for t in [rng.normal(0, 0.5, 6) for _ in range(20)] + [np.zeros(6), np.array([1e-9, -2e-9, 1e-9, 1, 2, 3])]:
+        T = velo.api.pose_vec2mat(t)
+        np.testing.assert_allclose(T[:3, :3], Rotation.from_rotvec(t[:3]).as_matrix(), atol=1e-14)
+        assert np.array_equal(T[:3, 3], t[3:]) and np.array_equal(T[3], [0, 0, 0, 1])

@@ -2,6 +2,8 @@
 
 Both are plain shared libraries with a C ABI (include/velo_gpu.h); no torch headers are involved.
 """
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -21,6 +23,26 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off",   # host code decides calibration / pose constants bit for bit
     "-shared", "-cudart", "static",
 ]
+
+
+@contextlib.contextmanager
+def _build_lock(out):
+    """One builder at a time per output (eight ranks of one torchrun import this package at once); the others wait and then find
+    the output fresh."""
+    with open(out + ".lock", "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
+def _run_to(cmd, out):
+    """run a compiler command whose last two arguments are `-o out`, writing to a temporary name and renaming (a reader never sees
+    a half-written library)"""
+    tmp = f"{out}.tmp.{os.getpid()}"
+    subprocess.run(cmd[:-1] + [tmp], check=True)
+    os.replace(tmp, out)
 
 
 def _newer(out, srcs):
@@ -51,10 +73,13 @@ def build_gpu(force=False, verbose=False):
         if os.path.isfile(GPU_LIB):
             return GPU_LIB  # prebuilt library shipped with the snapshot
         raise RuntimeError("nvcc not found and libvelo_gpu.so is not built")
-    extra = os.environ.get("VELO_NVCC_EXTRA", "").split()      # tuning experiments only (tools/)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
-        "-I", os.path.join(ROOT, "include"), "-I", CSRC] + gpu_sources() + ["-o", GPU_LIB]
-    subprocess.run(cmd, check=True)
+    with _build_lock(GPU_LIB):
+        if not force and _newer(GPU_LIB, gpu_deps()):
+            return GPU_LIB      # another process built it while this one waited
+        extra = os.environ.get("VELO_NVCC_EXTRA", "").split()      # tuning experiments only (tools/)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
+            "-I", os.path.join(ROOT, "include"), "-I", CSRC] + gpu_sources() + ["-o", GPU_LIB]
+        _run_to(cmd, GPU_LIB)
     return GPU_LIB
 
 
@@ -64,7 +89,10 @@ def build_synth(force=False):
         return SYNTH_LIB
     if shutil.which("gcc") is None and os.path.isfile(SYNTH_LIB):
         return SYNTH_LIB
-    subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-o", SYNTH_LIB, src, "-lm"], check=True)
+    with _build_lock(SYNTH_LIB):
+        if not force and _newer(SYNTH_LIB, [src]):
+            return SYNTH_LIB
+        _run_to(["gcc", "-O2", "-fPIC", "-shared", "-Wall", src, "-lm", "-o", SYNTH_LIB], SYNTH_LIB)
     return SYNTH_LIB
 
 

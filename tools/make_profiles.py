@@ -6,10 +6,14 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 
 shutil.copy(os.path.join(G, "final_bench.json"), os.path.join(P, f"{tag}_bench.json"))
 shutil.copy(os.path.join(G, "final_ref.json"), os.path.join(P, f"{tag}_bench_reference_arm.json"))
+for src, dst in (("final_bench_spec.json", "bench_pose_spread_spec.json"), ("final_bench_xyz.json", "bench_scan_format_xyz.json"),
+                 ("final_bench_offroad.json", "bench_offroad_rig.json"), ("final_next_rows.jsonl", "next_rows.jsonl")):
+    if os.path.isfile(os.path.join(G, src)) and os.path.getsize(os.path.join(G, src)) > 0:
+        shutil.copy(os.path.join(G, src), os.path.join(P, f"{tag}_{dst}"))
 
 # ---- launch list (ncu --metrics gpu__time_duration.sum --clock-control none) + per-kernel shares
 rows = [r for r in csv.reader(open(os.path.join(G, "final_launches.csv"))) if r and r[0].isdigit()]
@@ -57,7 +61,8 @@ m = {k: v[i].replace(",", "") for i, k in enumerate(h)}; mu = {k: u[i] for i, k 
 def to_bytes(k):
     s = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[mu[k]]; return float(m[k]) * s
 rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
-json.dump({"kernel": "icp_pass", "frames": 1000, "dram_bytes_per_launch": int(rd + wr), "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
+json.dump({"kernel": "icp_pass", "frames": 1000, "pose_spread": "tight", "dram_bytes_per_launch": int(rd + wr), "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
+           "warp_instructions": int(float(m["smsp__inst_executed.sum"])),
            "source": f"profiles/{tag}_icp_pass_ncu_raw.csv (ncu --set full --clock-control none, bench.py --frames 1000 --steps 1 --warmup 0)"},
           open(os.path.join(P, "traffic.json"), "w"))
 print(open(os.path.join(P, f"{tag}_launches_summary.txt")).read()); print(lines[:1500]); print(open(os.path.join(P, "traffic.json")).read())

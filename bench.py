@@ -265,6 +265,7 @@ def run_ours(args, rank, world, local_rank):
     # while the GPU already works on step k+1; every gather completes inside the timed region.
     icp_b = pool.zeros(icp.shape, np.float64) if dist is not None else icp
     gather = shard.RowGather(dist, T, icp.shape[1:], np.float64, dst=0, group=host_group) if dist is not None else None
+    gathered = None
     for _ in range(2):
         ctx.batch_frontend(0, batch, args.chunk, icp, vis, hd, nh)
     barrier()

@@ -151,6 +151,9 @@ int  velo_gpu_profile_enable(velo_gpu_ctx *ctx, int on);
 int  velo_gpu_profile_reset(velo_gpu_ctx *ctx);
 int  velo_gpu_profile_read(velo_gpu_ctx *ctx, float ms[VELO_NUM_KERNELS], int launches[VELO_NUM_KERNELS]); /* synchronises */
 const char *velo_gpu_kernel_name(int k);
+/* search statistics of the correspondence kernel (diagnostics, off by default: 1.6 % of the kernel): slots 60..62 of every
+ * normal-equation record = candidate distance evaluations, target rings scanned, ring-mask bits taken, summed over the pass's queries */
+int  velo_gpu_search_stats_enable(velo_gpu_ctx *ctx, int on);
 
 /* ---------------------------------------------------------------- single-frame path (drop-in) */
 /* ScanData ctor (lru.h:12-28): loadPoints layout (kitti.h:121-152) -> segmentPoints (kitti.h:154-185)

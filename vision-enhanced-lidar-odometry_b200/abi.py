@@ -94,7 +94,7 @@ EXPORTS = [
     "velo_gpu_abi_version", "velo_gpu_default_params", "velo_gpu_calib_from_kitti", "velo_pixel2canonical",
     "velo_canonical2pixel", "velo_kitti_load_calib", "velo_kitti_load_scan", "velo_kitti_format_pose", "velo_gpu_create", "velo_gpu_destroy", "velo_gpu_last_error", "velo_gpu_sync",
     "velo_gpu_device_name", "velo_gpu_host_alloc", "velo_gpu_host_free", "velo_gpu_timer_begin", "velo_gpu_timer_end",
-    "velo_gpu_profile_enable", "velo_gpu_profile_reset", "velo_gpu_profile_read", "velo_gpu_kernel_name",
+    "velo_gpu_profile_enable", "velo_gpu_search_stats_enable", "velo_gpu_profile_reset", "velo_gpu_profile_read", "velo_gpu_kernel_name",
     "velo_gpu_scan_upload", "velo_gpu_scan_upload_rings", "velo_gpu_projection_upload", "velo_gpu_scan_info", "velo_gpu_scan_download", "velo_gpu_project",
     "velo_gpu_project_download", "velo_gpu_depth_assoc", "velo_gpu_assoc_upload", "velo_gpu_f2f_selection", "velo_pose_vec2mat", "velo_gpu_icp_pass", "velo_gpu_icp_passes", "velo_gpu_visual_residuals", "velo_gpu_frame_to_frame", "velo_gpu_batch_frame_to_frame", "velo_gpu_match_hamming", "velo_gpu_triangulate",
     "velo_gpu_batch_upload", "velo_gpu_batch_run", "velo_gpu_batch_download", "velo_gpu_batch_frontend", "velo_gpu_launch_count",

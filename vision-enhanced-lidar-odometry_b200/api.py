@@ -25,7 +25,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build_gpu()
+    path = os.environ.get("VELO_GPU_LIB") or _build.build_gpu()      # VELO_GPU_LIB: a prebuilt tuning variant (tools/build_variants.py)
     L = C.CDLL(path)
     L.velo_gpu_last_error.restype = C.c_char_p
     L.velo_gpu_last_error.argtypes = [_P]
@@ -46,6 +46,7 @@ def lib():
     L.velo_gpu_host_free.argtypes = [_P]
     L.velo_gpu_timer_end.argtypes = [_P, C.POINTER(C.c_float)]
     L.velo_gpu_profile_enable.argtypes = [_P, C.c_int]
+    L.velo_gpu_search_stats_enable.argtypes = [_P, C.c_int]
     L.velo_gpu_profile_read.argtypes = [_P, _P, _P]
     L.velo_gpu_scan_upload.argtypes = [_P, C.c_int, _P, C.c_int]
     L.velo_gpu_scan_upload_rings.argtypes = [_P, C.c_int, _P, _P, C.c_int]
@@ -216,6 +217,9 @@ class Context:
 
     def profile(self, on):
         self._ck(self.L.velo_gpu_profile_enable(self.h, int(on)))
+
+    def search_stats(self, on):
+        self._ck(self.L.velo_gpu_search_stats_enable(self.h, int(on)))
 
     def profile_reset(self):
         self._ck(self.L.velo_gpu_profile_reset(self.h))

@@ -58,6 +58,7 @@ struct velo_gpu_ctx {
     // timing
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool profile = false;
+    bool search_stats = false;     // k_icp_pass also counts candidates / rings per pass (velo_gpu_search_stats_enable)
     std::vector<cudaEvent_t> ev_pool;
     std::vector<ProfRec> recs;
     cudaEvent_t cur_a = nullptr;
@@ -390,6 +391,7 @@ extern "C" int velo_gpu_timer_end(velo_gpu_ctx *ctx, float *ms) {
     return VELO_OK;
 }
 extern "C" int velo_gpu_profile_enable(velo_gpu_ctx *ctx, int on) { if (!ctx) return VELO_ERR_INVALID_ARG; ctx->profile = on != 0; return VELO_OK; }
+extern "C" int velo_gpu_search_stats_enable(velo_gpu_ctx *ctx, int on) { if (!ctx) return VELO_ERR_INVALID_ARG; ctx->search_stats = on != 0; return VELO_OK; }
 extern "C" int velo_gpu_profile_reset(velo_gpu_ctx *ctx) {
     if (!ctx) return VELO_ERR_INVALID_ARG;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -647,7 +649,7 @@ extern "C" int velo_gpu_icp_passes(velo_gpu_ctx *ctx, int slot_M, int slot_S, co
     const int ctas = auto_ctas(ctx, 1, ctx->icp_partial_ctas);
     // every query writes its record in every pass, so the records need no clearing
     launch_icp(launcher(ctx), ctx->B, ctx->dcal, sc_d_icp(ctx), 1, n_passes, ctas, sc_icp_partial(ctx), sc_icp_out(ctx), ctx->B.P,
-               corr ? ctx->d_corr : nullptr, corr ? ctx->B.N : 0);
+               corr ? ctx->d_corr : nullptr, corr ? ctx->B.N : 0, nullptr, 0, ctx->search_stats);
     CK(cudaGetLastError());
     std::vector<double> out((size_t)n_passes * VELO_NEQ_STRIDE);
     CK(cudaMemcpyAsync(out.data(), sc_icp_out(ctx), out.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1131,7 +1133,7 @@ static int run_stages(velo_gpu_ctx *ctx, const Launcher &L, int slot0, int count
         if (skip_first) CK(cudaMemsetAsync(ctx->d_icp_out + (size_t)slot0 * B.P * VELO_NEQ_STRIDE, 0, (size_t)B.P * VELO_NEQ_STRIDE * sizeof(double), st));
         launch_icp(L, B, ctx->dcal, ctx->d_icp_units + s_first, n_units, ctx->batch_passes, ctas,
                    ctx->d_icp_partial + (size_t)s_first * launch_icp_runs_cap(B.N) * VELO_MAX_PASSES * 64,
-                   ctx->d_icp_out + (size_t)s_first * B.P * VELO_NEQ_STRIDE, B.P, nullptr);
+                   ctx->d_icp_out + (size_t)s_first * B.P * VELO_NEQ_STRIDE, B.P, nullptr, 0, nullptr, 0, ctx->search_stats);
     }
     if ((stages & VELO_STAGE_VISUAL) && pairs > 0 && ctx->batch_vis > 0) {
         const int V = ctx->prm.f2f_iterations;

@@ -143,7 +143,7 @@ void launch_assoc(const Launcher &L, const DevBuffers &B, const DevCalib &cal, i
 int launch_icp_runs_cap(int max_points);
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
                 double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride = 0,
-                IcpFrozen *frozen = nullptr, int frozen_stride = 0);
+                IcpFrozen *frozen = nullptr, int frozen_stride = 0, bool stats = false);
 void launch_visual(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const VisUnit *units, int n_units, VisTun tun,
                    const int *lm_valid, const float4 *lm_xyz, double *partial, double *out, VisMatchOut *match_out, int ctas,
                    VisFixed fx = VisFixed{ nullptr, nullptr, nullptr, 0, 0 }, int *bad_flag = nullptr);

@@ -36,6 +36,12 @@
 #ifndef ICP_LEVMUL
 #define ICP_LEVMUL 4.0f        /* growth of the tolerance from level to level (2.0 measured 1 % slower) */
 #endif
+#ifndef ICP_CELLSEED
+#define ICP_CELLSEED 1         /* cell seeds: 0 off, 1 first pass of a frame pair, 3 whenever the previous pass left no pair (measured 1 % slower than 1) */
+#endif
+#ifndef ICP_CELLSEED_TOL
+#define ICP_CELLSEED_TOL 0.006f /* elevation tolerance (rad) of the rings a cell seed is taken from (about one ring spacing wide in total) */
+#endif
 #define VELO_STR_(x) #x
 #define VELO_UNROLL(n) _Pragma(VELO_STR_(unroll n))
 #define KEY_INF 0xFFFFFFFFFFFFFFFFull
@@ -46,16 +52,6 @@ __device__ __forceinline__ u64 make_key(float d2, int ring, int idx) {
 __device__ __forceinline__ int key_ring(u64 k) { return (int)(((unsigned)k) >> VELO_IDX_BITS); }
 __device__ __forceinline__ int key_idx(u64 k) { return (int)(((unsigned)k) & ((1u << VELO_IDX_BITS) - 1u)); }
 __device__ __forceinline__ float key_d2(u64 k) { return __uint_as_float((unsigned)(k >> 32)); }
-
-// best two rings under re-visits of the same ring
-__device__ __forceinline__ void merge_key(u64 k, u64 &ki, u64 &kj) {
-    if (k == KEY_INF) return;
-    const int r = key_ring(k);
-    if (r == key_ring(ki)) { if (k < ki) ki = k; }
-    else if (r == key_ring(kj)) { if (k < kj) kj = k; if (kj < ki) { u64 t = ki; ki = kj; kj = t; } }
-    else if (k < ki) { kj = ki; ki = k; }
-    else if (k < kj) kj = k;
-}
 
 struct Window { int b0, b1; bool wrapped, full; float gam, half; };
 
@@ -150,7 +146,9 @@ __host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(
 // carrying the dead record code)
 // W1 = true: at most 64 rings, i.e. ring masks of ONE 64-bit word: the word loops and the visited-mask array disappear at compile
 // time (the array otherwise lives in local memory because it is indexed by a runtime word number; measured 4 % of the kernel).
-template <bool RECORDS, bool W1>
+// STATS = true: candidates / rings / mask bits per pass are counted into slots 60..62 of the records (1.6 % of the kernel; off by default,
+// velo_gpu_search_stats_enable)
+template <bool RECORDS, bool W1, bool STATS>
 __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
                                                           double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
                                                           IcpFrozen *__restrict__ frozen, int frozen_stride) {
@@ -162,12 +160,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     __shared__ unsigned s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];             // per warp and run: no atomics
     __shared__ IcpPass s_pass[VELO_MAX_PASSES];
     __shared__ int s_next;
-    if (threadIdx.x == 0) s_next = 0;
+    __shared__ double s_loss[4];                       // loss constants of the unit: a^2, 1/a^2, w a^2/2, w
     const IcpUnit &U = units[blockIdx.y];
+    if (threadIdx.x == 0) { s_next = 0; const double bb = U.loss_a * U.loss_a; s_loss[0] = bb; s_loss[1] = 1.0 / bb; s_loss[2] = 0.5 * U.weight * bb; s_loss[3] = U.weight; }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NP = U.n_pass;
     if (U.src_slot < 0) return;   // unit without a previous scan: contributes nothing (k_neq_reduce writes its zeros)
-    const int nrM = B.n_rings[U.src_slot];
+    const int nrM = B.n_rings[U.src_slot], nrS = B.n_rings[U.tgt_slot];
     const int *rsM = B.ring_start + (size_t)U.src_slot * (B.R + 1);
     const int *rsS = B.ring_start + (size_t)U.tgt_slot * (B.R + 1);
     const int skip = U.skip;
@@ -260,19 +259,42 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             const float az = atan2_q(vy, vx), el = atan2_q(vz, D);
 
             u64 ki = KEY_INF, kj = KEY_INF;
+            // Seeds only BOUND the search: two real target points of different rings within the threshold => the runner-up is at most as
+            // far as the farther of them.  The search below starts from empty (ki, kj), visits every ring once and finds the seed points
+            // again (they lie inside the window their own distance defines), so ring results merge without any same-ring case.
+            float seed_bound = thr_f;
             if (active) {
-                // seeds from the previous pass: the two points it chose are real target points => valid bounds
-                if (pki != KEY_INF) {
-                    const int s = key_ring(pki), n = key_idx(pki);
-                    const float4 c = __ldg(ptsS + RS_S(s) + n);
-                    const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
-                    if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
+                if (pkj != KEY_INF) {                   // the pair the previous pass of this frame pair chose
+                    const float4 ca = __ldg(ptsS + RS_S(key_ring(pki)) + key_idx(pki)), cb = __ldg(ptsS + RS_S(key_ring(pkj)) + key_idx(pkj));
+                    const float m = fmaxf(d2f(ca.x, ca.y, ca.z, mx, my, mz), d2f(cb.x, cb.y, cb.z, mx, my, mz));
+                    if (m <= thr_f) seed_bound = m;
                 }
-                if (pkj != KEY_INF) {
-                    const int s = key_ring(pkj), n = key_idx(pkj);
-                    const float4 c = __ldg(ptsS + RS_S(s) + n);
-                    const float d2 = d2f(c.x, c.y, c.z, mx, my, mz);
-                    if (d2 <= thr_f) merge_key(make_key(d2, s, n), ki, kj);
+                // Cell seeds (first pass of a frame pair, no pair yet): the target point stored for the query's own azimuth bin in the
+                // two rings nearest its elevation — two cell lookups and two points instead of a search that starts from the full
+                // threshold radius (measured: 180 -> 81 candidates per first-pass query).
+                if ((ICP_CELLSEED == 1 && ps == 0) || (ICP_CELLSEED == 3 && pkj == KEY_INF)) {
+                    const int b = az_bin(az);
+                    const int base = (b / VELO_BINS_PER_SECTOR) * VELO_EL_BUCKETS;
+                    const int eb0 = el_bucket(el - ICP_CELLSEED_TOL), eb1 = el_bucket(el + ICP_CELLSEED_TOL);
+                    int s1 = -1, s2 = -1;
+                    for (int wd = 0; wd < W && s2 < 0; wd++) {
+                        u64 m = __ldg(mloS + (size_t)(base + eb1) * W + wd) & __ldg(mhiS + (size_t)(base + eb0) * W + wd);
+                        if (m != 0ull && s1 < 0) { s1 = wd * 64 + __ffsll((long long)m) - 1; m &= m - 1; }
+                        if (m != 0ull && s1 >= 0) s2 = wd * 64 + __ffsll((long long)m) - 1;
+                    }
+                    if (s1 >= 0 && s2 < 0) s2 = (s1 + 1 < nrS) ? s1 + 1 : s1 - 1;
+                    if (s1 >= 0 && s2 >= 0) {
+                        const int *csa = csS + s1 * (VELO_AZ_BINS + 1) + b, *csb = csS + s2 * (VELO_AZ_BINS + 1) + b;
+                        const int a0 = __ldg(csa), a1 = __ldg(csa + 1), b0 = __ldg(csb), b1 = __ldg(csb + 1);
+                        if (a1 > a0 && b1 > b0) {
+                            // nearest point of either cell (a cell holds about two points; the order inside a cell is not fixed, a minimum is)
+                            float da = CUDART_INF_F, db = CUDART_INF_F;
+                            for (int p = a0; p < a1; p++) { const float4 c = __ldg(sorted + p); da = fminf(da, d2f(c.x, c.y, c.z, mx, my, mz)); }
+                            for (int p = b0; p < b1; p++) { const float4 c = __ldg(sorted + p); db = fminf(db, d2f(c.x, c.y, c.z, mx, my, mz)); }
+                            const float m = fmaxf(da, db);
+                            if (m <= thr_f) seed_bound = m;
+                        }
+                    }
                 }
             }
             // Exhaustive search: every ring that can hold a point within the current bound on d2_j (velo.h:825-848) is visited exactly
@@ -282,7 +304,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
             // removed: without it the unseeded pass evaluates 164 instead of 74 candidates per query and the kernel is 7 % faster.)
             // Written as a warp-synchronous "advance / scan" loop: lanes first advance (cheap ring tests) until each holds a
             // candidate range, then all of them scan together, so the distance loop runs converged.
-            float bound = (kj == KEY_INF) ? thr_f : fminf(thr_f, key_d2(kj));
+            float bound = seed_bound;
             Window w = make_window(bound, az, D, rho);
             {
                 u64 V[4] = { 0ull, 0ull, 0ull, 0ull };
@@ -327,8 +349,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                             st_rings++; have = false;
                             if (scan_found(best, thr_excl)) {
                                 const u64 oj = kj;
-                                merge_key(scan_key(best, s_cur), ki, kj);
-                                if (kj != oj) { bound = fminf(thr_f, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
+                                {   // every ring is visited once: plain insertion into the two smallest keys, branch-free
+                                    const u64 k = scan_key(best, s_cur), lo = min(k, ki), hi = max(k, ki);
+                                    ki = lo; kj = min(kj, hi);
+                                }
+                                if (kj != oj) { bound = fminf(seed_bound, key_d2(kj)); if (!tight) w = make_window(bound, az, D, rho); }
                             }
                         }
                     }
@@ -373,18 +398,19 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                         double y0, y1, y2;
                         ICP_ROTATE(y0, y1, y2)
                         const double m0 = y0 + (P.pose.t[0] - (double)v0.x), m1 = y1 + (P.pose.t[1] - (double)v0.y), m2 = y2 + (P.pose.t[2] - (double)v0.z);
-                        res = m0 * dnx + m1 * dny + m2 * dnz;
+                        // (f64 residual / Jacobian rows are compared at 1e-5 relative and agree to ~1e-15 either way: explicit fused multiply-adds)
+                        res = fma(m0, dnx, fma(m1, dny, m2 * dnz));
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
                             const double *d = P.pose.dR + 9 * k;
-                            const double e0 = d[0] * x0 + d[1] * x1 + d[2] * x2, e1 = d[3] * x0 + d[4] * x1 + d[5] * x2, e2 = d[6] * x0 + d[7] * x1 + d[8] * x2;
-                            J[k] = e0 * dnx + e1 * dny + e2 * dnz;
+                            const double e0 = fma(d[0], x0, fma(d[1], x1, d[2] * x2)), e1 = fma(d[3], x0, fma(d[4], x1, d[5] * x2)), e2 = fma(d[6], x0, fma(d[7], x1, d[8] * x2));
+                            J[k] = fma(e0, dnx, fma(e1, dny, e2 * dnz));
                         }
                         J[3] = dnx; J[4] = dny; J[5] = dnz;
                         // ScaledLoss(CauchyLoss(a), w) (velo.h:885-891)
-                                                const double bb = U.loss_a * U.loss_a, cc = 1.0 / bb, sum = 1.0 + res * res * cc, inv = 1.0 / sum;
-                        rho1 = U.weight * fmax(2.2250738585072014e-308, inv);
-                        rho0h = 0.5 * U.weight * bb * log(sum);
+                        const double sum = 1.0 + res * res * s_loss[1], inv = 1.0 / sum;
+                        rho1 = s_loss[3] * fmax(2.2250738585072014e-308, inv);
+                        rho0h = s_loss[2] * log(sum);
                         rec.kept = 1; rec.residual = res;
                         kept = true;
                     }
@@ -439,14 +465,13 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                 } else if (fr == 6 && c0 == 6) { rec[27] += ch; rec[55] += 0.5 * cr0; }
             }
 #endif
-            {   // search statistics of the pass: one REDUX per counter, lane 0 adds them to the warp's own counters
+            {   // kept count of the pass; with STATS also the search statistics (one REDUX per counter, lane 0 adds them to the warp's own counters)
                 const unsigned r_kept = __popc(__ballot_sync(FULL, kept));
-                const unsigned r_seed = 0u, r_exh = __reduce_add_sync(FULL, (unsigned)st_exh);
-                const unsigned r_rings = __reduce_add_sync(FULL, (unsigned)st_rings), r_mask = __reduce_add_sync(FULL, (unsigned)st_mask);
-                if (lane == 0) {
-                    unsigned *st = s_stat[wid][ps];
-                    st[0] += r_kept; st[1] += r_seed; st[2] += r_exh; st[3] += r_rings; st[4] += r_mask;
-                }
+                if (STATS) {
+                    const unsigned r_exh = __reduce_add_sync(FULL, (unsigned)st_exh);
+                    const unsigned r_rings = __reduce_add_sync(FULL, (unsigned)st_rings), r_mask = __reduce_add_sync(FULL, (unsigned)st_mask);
+                    if (lane == 0) { unsigned *st = s_stat[wid][ps]; st[0] += r_kept; st[2] += r_exh; st[3] += r_rings; st[4] += r_mask; }
+                } else if (lane == 0) s_stat[wid][ps][0] += r_kept;
             }
         }
       }
@@ -502,16 +527,16 @@ __global__ void __launch_bounds__(256) k_neq_reduce(DevBuffers B, const IcpUnit 
 int launch_icp_runs_cap(int max_points) { return icp_runs_cap(max_points); }
 
 void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, const IcpUnit *units, int n_units, int n_pass, int ctas,
-                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride, IcpFrozen *frozen, int frozen_stride) {
+                double *partial, double *out, int out_stride_passes, velo_icp_corr *corr, int corr_stride, IcpFrozen *frozen, int frozen_stride, bool stats) {
     if (n_units <= 0) return;
     const int runs_cap = icp_runs_cap(B.N);
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
     const bool rec = corr || frozen, w1 = B.W == 1;
-    if (rec && w1) k_icp_pass<true, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
-    else if (rec) k_icp_pass<true, false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
-    else if (w1) k_icp_pass<false, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, nullptr, 0, nullptr, 0);
-    else k_icp_pass<false, false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, nullptr, 0, nullptr, 0);
+#define ICP_LAUNCH(R_, W_, S_) k_icp_pass<R_, W_, S_><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0)
+    if (stats) { if (rec && w1) ICP_LAUNCH(true, true, true); else if (rec) ICP_LAUNCH(true, false, true); else if (w1) ICP_LAUNCH(false, true, true); else ICP_LAUNCH(false, false, true); }
+    else { if (rec && w1) ICP_LAUNCH(true, true, false); else if (rec) ICP_LAUNCH(true, false, false); else if (w1) ICP_LAUNCH(false, true, false); else ICP_LAUNCH(false, false, false); }
+#undef ICP_LAUNCH
     if (L.post) L.post(L.user, VK_ICP_PASS);
     dim3 g2(n_units, n_pass);
     if (L.pre) L.pre(L.user, VK_NEQ_REDUCE);

@@ -73,7 +73,7 @@ typedef struct velo_gpu_params {
     int max_matches;              /* per camera per frame pair */
     int max_icp_passes;           /* f2f_iterations * icp_iterations per batched call */
     int ctas_per_icp_unit;        /* CTAs sharing the queries of one frame pair (all its passes); 0 = auto.  Results do not depend on it:
-                                     sums are kept per run of 128 queries and added in run order */
+                                     sums are kept per run of 64 queries and added in run order */
     int reserved1;
 } velo_gpu_params;
 

@@ -314,7 +314,7 @@ def test_batched_path_equals_single_frame_path_and_oracle(velo, oracle, calib):
 
 
 def test_normal_equations_do_not_depend_on_the_launch_shape(velo, calib):
-    """sums are kept per run of 128 queries and added in run order, so the CTAs per frame pair (and hence which warp processed
+    """sums are kept per run of 64 queries and added in run order, so the CTAs per frame pair (and hence which warp processed
     which run) must not change a single bit of the result"""
     outs = []
     for ctas in (0, 1, 5, 32):

@@ -10,7 +10,7 @@ def atan2_q(y, x):
     a = np.where(mx > 0, mn / np.where(mx > 0, mx, 1), 0).astype(f)
     s = (a * a).astype(f)
     p = np.full_like(a, c[5])
-    for k in range(4, -1, -1): p = ((p * s).astype(f) + c[k]).astype(f)
+    for k in range(4, -1, -1): p = (p.astype(np.float64) * s.astype(np.float64) + np.float64(c[k])).astype(f)      # fmaf: the product is exact in f64
     r = (p * a).astype(f)
     r = np.where(ay > ax, (f(np.pi / 2) - r).astype(f), r)
     r = np.where(x < 0, (f(np.pi) - r).astype(f), r)

@@ -49,23 +49,27 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_w, int &total) {
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
+// ---- pruning geometry (index frame, azimuth / elevation / range of a point).  None of it decides an output bit: it only sizes and
+// places conservative search windows, whose pads (asin_ub, mask_query, INDEX_EL_PAD) cover its error.  So, unlike the parity-critical
+// arithmetic, it uses fused multiply-adds and the 2-ulp hardware square root / division.
+__device__ __forceinline__ float sqrt_ap(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void idx_frame(const DevCalib &cal, float x, float y, float z, float &vx, float &vy, float &vz) {
-    float dx = x - cal.vtc[3], dy = y - cal.vtc[7], dz = z - cal.vtc[11];
-    vx = cal.vtc[0] * dx + cal.vtc[4] * dy + cal.vtc[8] * dz;
-    vy = cal.vtc[1] * dx + cal.vtc[5] * dy + cal.vtc[9] * dz;
-    vz = cal.vtc[2] * dx + cal.vtc[6] * dy + cal.vtc[10] * dz;
+    const float dx = x - cal.vtc[3], dy = y - cal.vtc[7], dz = z - cal.vtc[11];
+    vx = fmaf(cal.vtc[0], dx, fmaf(cal.vtc[4], dy, cal.vtc[8] * dz));
+    vy = fmaf(cal.vtc[1], dx, fmaf(cal.vtc[5], dy, cal.vtc[9] * dz));
+    vz = fmaf(cal.vtc[2], dx, fmaf(cal.vtc[6], dy, cal.vtc[10] * dz));
 }
-// atan2 for the *pruning* geometry of a query (azimuth / elevation in the index frame): odd minimax polynomial of degree 11 on
-// [0,1] + octant fix-up, |error| < 2e-6 rad over all quadrants (checked against f64 atan2 on 2.4e7 points, tools/check_atan2.py);
-// asin_ub() pads every window by 1e-5 rad for it.  About a third of the instructions of atan2f.  Index *construction* keeps atan2f.
+// atan2 for the *pruning* geometry (azimuth / elevation in the index frame): odd minimax polynomial of degree 11 on [0,1] + octant
+// fix-up, |error| < 2.5e-6 rad over all quadrants (checked against f64 atan2, tools/check_atan2.py, tests/test_abi_host.py);
+// asin_ub() pads every window by 1e-5 rad for it.  About a third of the instructions of atan2f.
 __device__ __forceinline__ float atan2_q(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
     const float a = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
     const float s = a * a;
     float p = -0.011719132173485577f;
-    p = p * s + 0.05264734316289409f; p = p * s - 0.11642647568056484f; p = p * s + 0.1935403746008874f;
-    p = p * s - 0.3326228279880411f; p = p * s + 0.9999772191230201f;
+    p = fmaf(p, s, 0.05264734316289409f); p = fmaf(p, s, -0.11642647568056484f); p = fmaf(p, s, 0.1935403746008874f);
+    p = fmaf(p, s, -0.3326228279880411f); p = fmaf(p, s, 0.9999772191230201f);
     float r = p * a;
     if (ay > ax) r = 1.57079632679489662f - r;
     if (x < 0.f) r = 3.14159265358979324f - r;

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(256) k_ingest_permute(DevBuffers B, DevCalib c
 #define INDEX_KEEP 8          /* points per thread whose bin stays in a register (rings up to 2048 points) */
 __device__ __forceinline__ int index_bin_of(const DevCalib &cal, const float4 &p, float &el, float &rho) {
     float vx, vy, vz; idx_frame(cal, p.x, p.y, p.z, vx, vy, vz);
-    const float dxy2 = vx * vx + vy * vy;
-    el = atan2_q(vz, sqrtf(dxy2)); rho = sqrtf(dxy2 + vz * vz);
+    const float dxy2 = fmaf(vx, vx, vy * vy);
+    el = atan2_q(vz, sqrt_ap(dxy2)); rho = sqrt_ap(fmaf(vz, vz, dxy2));
     return az_bin(atan2_q(vy, vx));
 }
 __global__ void __launch_bounds__(256) k_index_build(DevBuffers B, DevCalib cal, int slot0) {

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                             for (int p = a0; p < a1; p++) { const float4 c = __ldg(sorted + p); da = fminf(da, d2f(c.x, c.y, c.z, mx, my, mz)); }
                             for (int p = b0; p < b1; p++) { const float4 c = __ldg(sorted + p); db = fminf(db, d2f(c.x, c.y, c.z, mx, my, mz)); }
                             const float m = fmaxf(da, db);
-                            if (m <= thr_f) seed_bound = m;
+                            if (m < seed_bound) seed_bound = m;
                         }
                     }
                 }

@@ -1176,6 +1176,9 @@ extern "C" int velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, 
 }
 
 // upload -> run -> download of a whole batch with the uploads of chunk c+1 overlapping the kernels of chunk c
+// tuning aid (tools/): VELO_FE_UPLOAD_REPEAT=k copies every chunk k times, which puts one GPU into the copy-bound regime that eight
+// GPUs sharing a host are in
+static int fe_upload_repeat() { static const int r = [] { const char *e = getenv("VELO_FE_UPLOAD_REPEAT"); return e ? std::max(1, atoi(e)) : 1; }(); return r; }
 extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
                                        double *icp_neq, double *vis_neq, int *has_depth, int *n_hits) {
     if (!ctx || !in) return VELO_ERR_INVALID_ARG;
@@ -1185,6 +1188,8 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
     // geometrically up to count/8.  A chunk's kernels can only start when ALL of it has arrived, so a chunk must not take longer to
     // upload than its predecessor takes to compute: the growth factor is 0.9 x (time of the previous call / time of its uploads),
     // clamped to [1.15, 2] — 2 when the copies are fast (one GPU alone on the host: 55 GB/s), ~1.2 when eight GPUs share it (23 GB/s).
+    // (Measured with VELO_FE_UPLOAD_REPEAT / VELO_FE_TRACE: in the copy-bound regime the call ends 2.5 ms after the last copy, so
+    // chunks that shrink again towards the end buy nothing; the copy rate under load is what limits eight GPUs on one host.)
     std::vector<int> cut(1, 0);
     if (chunk > 0) { for (int i = chunk; i < count; i += chunk) cut.push_back(i); }
     else {
@@ -1213,6 +1218,9 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
     cudaEvent_t *ev_light = ctx->chunk_ev.data() + nchunks + 1;
     if (two) CK(cudaStreamWaitEvent(ctx->stream2, ctx->chunk_ev[nchunks], 0));
     const int light = VELO_STAGE_INGEST | VELO_STAGE_INDEX | VELO_STAGE_PROJECT | VELO_STAGE_ASSOC;
+    static const bool trace = getenv("VELO_FE_TRACE") != nullptr;       // tuning aid: per-chunk completion times on stderr
+    std::vector<cudaEvent_t> tr;
+    if (trace) { tr.resize(3 * (size_t)nchunks); for (auto &e : tr) cudaEventCreate(&e); }
     for (int c = 0; c < nchunks; c++) {
         cudaStream_t st = (two && (c & 1)) ? ctx->stream2 : ctx->stream;
         const Launcher L = launcher_on(ctx, st);
@@ -1220,19 +1228,33 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
         // before its kernels, so preparing chunk c+1 overlaps the device work of chunk c
         int rc = upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream);
         if (rc) return rc;
+        for (int rep = 1; rep < fe_upload_repeat(); rep++) upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream);
         CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+        if (trace) cudaEventRecord(tr[3 * c], ctx->copy_stream);
         CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
         rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], light, 1);
         if (rc) return rc;
         CK(cudaEventRecord(ev_light[c], st));
+        if (trace) cudaEventRecord(tr[3 * c + 1], st);
         if (c > 0) CK(cudaStreamWaitEvent(st, ev_light[c - 1], 0));
         rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], VELO_STAGE_ICP | VELO_STAGE_VISUAL, 1);
         if (rc) return rc;
+        if (trace) cudaEventRecord(tr[3 * c + 2], st);
     }
     CK(cudaEventRecord(ctx->fe_up1, ctx->copy_stream));
     if (two) { CK(cudaEventRecord(ev_light[nchunks], ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ev_light[nchunks], 0)); }
     ctx->launch_stream = ctx->stream;
     const int rc = velo_gpu_batch_download(ctx, slot0, count, icp_neq, vis_neq, has_depth, n_hits);
+    if (trace) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[fe] growth %.2f, %d chunks: size copy_done light_done icp_done (ms)\n", ctx->fe_growth, nchunks);
+        for (int c = 0; c < nchunks; c++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, ctx->fe_c0, tr[3 * c]); cudaEventElapsedTime(&b, ctx->fe_c0, tr[3 * c + 1]); cudaEventElapsedTime(&d, ctx->fe_c0, tr[3 * c + 2]);
+            fprintf(stderr, "[fe] %4d %8.2f %8.2f %8.2f\n", cut[c + 1] - cut[c], a, b, d);
+        }
+        for (auto &e : tr) cudaEventDestroy(e);
+    }
     if (rc == VELO_OK && chunk <= 0) {        // how fast the copies were against the whole call: the next call's chunk growth
         CK(cudaEventRecord(ctx->fe_c1, ctx->stream)); CK(cudaEventSynchronize(ctx->fe_c1)); CK(cudaEventSynchronize(ctx->fe_up1));
         float up = 0.f, all = 0.f;

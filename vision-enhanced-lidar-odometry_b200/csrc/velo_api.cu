@@ -1037,7 +1037,10 @@ static int check_range(velo_gpu_ctx *ctx, int slot0, int count) {
 }
 
 // copy the inputs of batch entries [i0, i0+count) (slots slot0+i0 ...) to the device on `st`
-static int upload_range(velo_gpu_ctx *ctx, int slot0_all, int i0, int count, const velo_batch_inputs *src, cudaStream_t st) {
+// st_clear: the stream that voids the old projections of the slots.  A memset is a (tiny) KERNEL: on a copy stream it would queue for
+// an SM slot behind the resident CTAs of the correspondence kernel (milliseconds each) and stall every copy issued after it — measured
+// as 28 instead of 50 GB/s once the GPU was busy — so the pipelined call gives the chunk's compute stream here.
+static int upload_range(velo_gpu_ctx *ctx, int slot0_all, int i0, int count, const velo_batch_inputs *src, cudaStream_t st, cudaStream_t st_clear) {
     const int slot0 = slot0_all + i0;
     velo_batch_inputs inl = *src, *in = &inl;
     {
@@ -1067,7 +1070,7 @@ static int upload_range(velo_gpu_ctx *ctx, int slot0_all, int i0, int count, con
         CK(cudaMemcpyAsync(B.n_points + slot0, in->n_points, count * sizeof(int), cudaMemcpyHostToDevice, st));
         for (int i = 0; i < count; i++) { ctx->h_npoints[slot0 + i] = in->n_points[i]; ctx->h_stride[slot0 + i] = (int)(rec / sizeof(float)); }
         CK(cudaMemcpyAsync(B.raw_stride + slot0, ctx->h_stride.data() + slot0, count * sizeof(int), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(B.proj_count + (size_t)slot0 * B.C * B.R, 0, (size_t)count * B.C * B.R * sizeof(int), st));   // projections of the old scans are void
+        CK(cudaMemsetAsync(B.proj_count + (size_t)slot0 * B.C * B.R, 0, (size_t)count * B.C * B.R * sizeof(int), st_clear));   // projections of the old scans are void
     }
     if (in->kp && in->n_kp) {
         const size_t per = VELO_NUM_KP_SETS * C;
@@ -1113,7 +1116,7 @@ extern "C" int velo_gpu_batch_upload(velo_gpu_ctx *ctx, int slot0, int count, co
     if (!ctx || !in) return VELO_ERR_INVALID_ARG;
     if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
-    return upload_range(ctx, slot0, 0, count, in, ctx->stream);
+    return upload_range(ctx, slot0, 0, count, in, ctx->stream, ctx->stream);
 }
 
 // the selected stages for slots [slot0, slot0 + count) on L.stream; partial-sum areas are addressed by slot, so launches for
@@ -1226,9 +1229,9 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
         const Launcher L = launcher_on(ctx, st);
         // host-side preparation of the chunk (pose packs: trigonometry + forward-mode dR per pass) and its copies are issued right
         // before its kernels, so preparing chunk c+1 overlaps the device work of chunk c
-        int rc = upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream);
+        int rc = upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream, st);
         if (rc) return rc;
-        for (int rep = 1; rep < fe_upload_repeat(); rep++) upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream);
+        for (int rep = 1; rep < fe_upload_repeat(); rep++) upload_range(ctx, slot0, cut[c], cut[c + 1] - cut[c], in, ctx->copy_stream, st);
         CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
         if (trace) cudaEventRecord(tr[3 * c], ctx->copy_stream);
         CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));

@@ -210,7 +210,9 @@ def run_ours(args, rank, world, local_rank):
     scan_bytes = int(batch.n_points.max()) * rec * (T + 1)          # rows of the longest scan, not max_points (velo_api.cu upload_range)
     h2d = scan_bytes + sum(a.nbytes for a in (batch.n_points, batch.kp, batch.n_kp, batch.matches, batch.n_matches)) \
         + (T + 1) * batch.n_passes * 400 + (T + 1) * batch.n_vis * 72
-    d2h = icp.nbytes + vis.nbytes + hd.nbytes + nh.nbytes
+    # keypoints_with_depth (what featureDepthAssociation hands its caller, velo.h:479) comes back too unless --no-kpwd
+    kw = None if args.no_kpwd else pool.zeros((T + 1, 2, prm.num_cams, prm.max_features, 4), np.float32)
+    d2h = icp.nbytes + vis.nbytes + hd.nbytes + nh.nbytes + (0 if kw is None else kw.nbytes)
 
     def barrier():
         ctx.sync()
@@ -267,13 +269,13 @@ def run_ours(args, rank, world, local_rank):
     gather = shard.RowGather(dist, T, icp.shape[1:], np.float64, dst=0, group=host_group) if dist is not None else None
     gathered = None
     for _ in range(2):
-        ctx.batch_frontend(0, batch, args.chunk, icp, vis, hd, nh)
+        ctx.batch_frontend(0, batch, args.chunk, icp, vis, hd, nh, kpwd=kw)
     barrier()
     t0 = time.perf_counter()
     ctx.timer_begin()
     for k in range(args.steps):
         buf = icp if (k & 1) == 0 else icp_b
-        ctx.batch_frontend(0, batch, args.chunk, buf, vis, hd, nh)     # one C call: chunked upload overlapping compute, then download
+        ctx.batch_frontend(0, batch, args.chunk, buf, vis, hd, nh, kpwd=kw)     # one C call: chunked upload overlapping compute, then download
         if gather is not None:
             gathered = gather.wait()                                   # rows of step k-1
             gather.start(buf[1:])
@@ -451,6 +453,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of two frames of the timed batch")
+    ap.add_argument("--no-kpwd", action="store_true", help="end-to-end call without the keypoints_with_depth clouds (128 MB of the D2H bytes at the defaults)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

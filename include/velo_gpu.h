@@ -301,6 +301,11 @@ int  velo_gpu_batch_run(velo_gpu_ctx *ctx, int slot0, int count, int stages, int
  * has_depth [count][sets][cams][max_features], n_hits [count][sets][cams]; any pointer may be NULL. Synchronises. */
 int  velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *icp_neq, double *vis_neq,
                              int *has_depth, int *n_hits);
+/* keypoints_with_depth of the batch (featureDepthAssociation's output cloud, velo.h:479-481): kpwd [count][sets][cams][max_features][4]
+ * floats {x, y, z, 1}; the first n_hits[slot][set][cam] records of an image are valid and has_depth[k] indexes them.  Optional: the
+ * batched frameToFrame consumes the cloud on the device.  (Per-query correspondence records exist per frame pair, velo_gpu_icp_passes:
+ * 128 B x queries x passes is not a batch-sized output.)  Synchronises. */
+int  velo_gpu_batch_download_kpwd(velo_gpu_ctx *ctx, int slot0, int count, float *kpwd);
 /* the whole front end for a batch in one call: upload (pinned host buffers) -> all stages -> download, with the upload of
  * chunk c+1 overlapping the kernels of chunk c on a second stream (chunk = frames per chunk; 0 = a small first chunk — the only
  * upload nothing can hide — then geometric growth up to count/8, the factor (1.15 .. 2) adapted from the previous call so that a
@@ -308,6 +313,10 @@ int  velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, double *ic
  * frame pair for it).  Results do not depend on the chunking.  Synchronises. */
 int  velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
                              double *icp_neq, double *vis_neq, int *has_depth, int *n_hits);
+/* the same call, also returning keypoints_with_depth (layout of velo_gpu_batch_download_kpwd): each chunk's cloud travels back on
+ * its own stream as soon as the chunk's association stage is done, under the kernels of the later chunks */
+int  velo_gpu_batch_frontend_kpwd(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
+                                  double *icp_neq, double *vis_neq, int *has_depth, int *n_hits, float *kpwd);
 /* number of kernel launches issued by this context since creation */
 int  velo_gpu_launch_count(velo_gpu_ctx *ctx, int64_t *launches);
 /* per-slot counts needed to state algorithmic bytes: n_points[count], n_rings[count],

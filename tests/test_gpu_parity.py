@@ -294,21 +294,27 @@ def test_batched_path_equals_single_frame_path_and_oracle(velo, oracle, calib):
                 np.testing.assert_allclose(vis[t, it, :56], ovis[t, it, :56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * sc)
                 assert vis[t, it, 56] == ovis[t, it, 56]
         # association results of the batch equal the oracle's
+        kw = c.batch_download_kpwd(0, 3)
         for t in range(3):
             pts, rs, _ = oracle.segment(b.scans[t, : b.n_points[t]], calib)
             for cam in range(prm.num_cams):
                 rc, proj, valid = oracle.project(pts, rs, calib, cam)
                 for s in range(2):
-                    ohd, _ = oracle.depth_assoc(valid, proj, rc, b.kp[t, s, cam])
+                    ohd, okw = oracle.depth_assoc(valid, proj, rc, b.kp[t, s, cam])
                     assert np.array_equal(hd[t, s, cam], ohd)
                     assert nh[t, s, cam] == (ohd >= 0).sum()
+                    assert kw[t, s, cam, : len(okw)].tobytes() == okw.tobytes()      # keypoints_with_depth of the batch (velo.h:479)
         npnt, nr, ptot, st = c.batch_counts(0, 3)
         assert np.array_equal(npnt, b.n_points) and np.all(nr == 64) and np.all(st == 0) and np.all(ptot > 10000)
         # the one-call pipelined path (chunked upload overlapping compute) gives byte-identical results
         for chunk in (1, 2, 0):
             icp2 = np.zeros_like(icp); vis2 = np.zeros_like(vis); hd2 = np.zeros_like(hd); nh2 = np.zeros_like(nh)
-            c.batch_frontend(0, b, chunk, icp2, vis2, hd2, nh2)
+            kw2 = np.zeros_like(kw)
+            c.batch_frontend(0, b, chunk, icp2, vis2, hd2, nh2, kpwd=kw2 if chunk != 2 else None)
             assert icp2.tobytes() == icp.tobytes() and vis2.tobytes() == vis.tobytes() and hd2.tobytes() == hd.tobytes() and nh2.tobytes() == nh.tobytes()
+            for t, sidx, cam in np.ndindex(3, 2, prm.num_cams):
+                n = nh[t, sidx, cam]
+                assert chunk == 2 or kw2[t, sidx, cam, :n].tobytes() == kw[t, sidx, cam, :n].tobytes()
     finally:
         c.close()
 
@@ -548,6 +554,30 @@ def test_random_ragged_ring_clouds(velo, oracle, calib, params, ctx):
             np.testing.assert_allclose(corr["residual"][k], ocorr["residual"][k], rtol=RTOL_RES, atol=1e-9)
             if kept:
                 np.testing.assert_allclose(neq[:56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max() + 1e-300)
+
+
+def test_icp_more_than_64_rings(velo, oracle, calib, params, ctx):
+    """100 target rings / 90 source rings (two 64-bit words of ring masks: the word loops of the cell seeds and of the search, rings
+    63 | 64 neighbours across the word boundary), dense in elevation so that a dozen rings lie inside the threshold; the fused
+    multi-pass launch (cell seeds in pass 0, the previous pair as the bound afterwards) against the oracle's brute force."""
+    from test_properties import _rings
+    rng = np.random.default_rng(77)
+    for quant in (None, 0.05):
+        ptsS, rsS = _rings(rng, 100, 60, quant)
+        ptsM, rsM = _rings(rng, 90, 40, quant)
+        ctx.scan_upload_rings(0, ptsS, rsS); ctx.scan_upload_rings(1, ptsM, rsM)
+        iters = [1, 1, 2]
+        poses = np.stack([np.concatenate([rng.normal(0, 0.01, 3), rng.normal(0, 0.05, 3)]) for _ in iters])
+        corr, neq = ctx.icp_passes(1, 0, poses, iters, 1)
+        for p, it in enumerate(iters):
+            ocorr, oneq, okept = oracle.icp_pass(ptsM, rsM, ptsS, rsS, poses[p], it, 1, params, 0)
+            assert corr.shape[1] == len(ocorr)
+            for f in ("src_ring", "src_idx", "kept", "np_s_i", "np_i", "np_s_j", "np_j", "np_k"):
+                assert np.array_equal(corr[p][f], ocorr[f]), (quant, p, f)
+            assert neq[p, 56] == okept and neq[p, 58] == len(ocorr)
+            if okept:
+                np.testing.assert_allclose(neq[p, :56], oneq[:56], rtol=RTOL_NEQ, atol=RTOL_NEQ * 1e-6 * np.abs(oneq[:56]).max() + 1e-300)
+        assert (ocorr["np_s_i"] >= 64).any() and (ocorr["np_s_i"] < 64).any()
 
 
 def test_depth_assoc_projection_larger_than_shared_memory(velo, oracle, calib, ctx):

@@ -97,6 +97,6 @@ EXPORTS = [
     "velo_gpu_profile_enable", "velo_gpu_search_stats_enable", "velo_gpu_profile_reset", "velo_gpu_profile_read", "velo_gpu_kernel_name",
     "velo_gpu_scan_upload", "velo_gpu_scan_upload_rings", "velo_gpu_projection_upload", "velo_gpu_scan_info", "velo_gpu_scan_download", "velo_gpu_project",
     "velo_gpu_project_download", "velo_gpu_depth_assoc", "velo_gpu_assoc_upload", "velo_gpu_f2f_selection", "velo_pose_vec2mat", "velo_gpu_icp_pass", "velo_gpu_icp_passes", "velo_gpu_visual_residuals", "velo_gpu_frame_to_frame", "velo_gpu_batch_frame_to_frame", "velo_gpu_match_hamming", "velo_gpu_triangulate",
-    "velo_gpu_batch_upload", "velo_gpu_batch_run", "velo_gpu_batch_download", "velo_gpu_batch_frontend", "velo_gpu_launch_count",
+    "velo_gpu_batch_upload", "velo_gpu_batch_run", "velo_gpu_batch_download", "velo_gpu_batch_download_kpwd", "velo_gpu_batch_frontend", "velo_gpu_batch_frontend_kpwd", "velo_gpu_launch_count",
     "velo_gpu_batch_counts",
 ]

@@ -46,6 +46,7 @@ def lib():
     L.velo_gpu_host_free.argtypes = [_P]
     L.velo_gpu_timer_end.argtypes = [_P, C.POINTER(C.c_float)]
     L.velo_gpu_profile_enable.argtypes = [_P, C.c_int]
+    L.velo_gpu_batch_download_kpwd.argtypes = [_P, C.c_int, C.c_int, _P]
     L.velo_gpu_search_stats_enable.argtypes = [_P, C.c_int]
     L.velo_gpu_profile_read.argtypes = [_P, _P, _P]
     L.velo_gpu_scan_upload.argtypes = [_P, C.c_int, _P, C.c_int]
@@ -70,6 +71,7 @@ def lib():
     L.velo_gpu_batch_run.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int]
     L.velo_gpu_batch_download.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
     L.velo_gpu_batch_frontend.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]
+    L.velo_gpu_batch_frontend_kpwd.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]
     L.velo_gpu_batch_counts.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P]
     L.velo_gpu_launch_count.argtypes = [_P, C.POINTER(C.c_int64)]
     if L.velo_gpu_abi_version() != abi.ABI_VERSION:
@@ -380,10 +382,21 @@ class Context:
     def batch_download(self, slot0, count, icp_neq=None, vis_neq=None, has_depth=None, n_hits=None):
         self._ck(self.L.velo_gpu_batch_download(self.h, slot0, count, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
 
-    def batch_frontend(self, slot0, batch, chunk=0, icp_neq=None, vis_neq=None, has_depth=None, n_hits=None):
+    def batch_download_kpwd(self, slot0, count, out=None):
+        """[count][sets][cams][max_features][4] float32; out may be a (pinned) array of that shape"""
+        if out is None:
+            out = np.zeros((count, abi.NUM_KP_SETS, self.prm.num_cams, self.prm.max_features, 4), np.float32)
+        self._ck(self.L.velo_gpu_batch_download_kpwd(self.h, slot0, count, _ptr(out)))
+        return out
+
+    def batch_frontend(self, slot0, batch, chunk=0, icp_neq=None, vis_neq=None, has_depth=None, n_hits=None, kpwd=None):
         bi = abi.BatchInputs(_ptr(batch.scans), _ptr(batch.n_points), _ptr(batch.kp), _ptr(batch.n_kp), _ptr(batch.matches), _ptr(batch.n_matches),
                              _ptr(batch.icp_poses), _ptr(batch.pass_iter), batch.n_passes, _ptr(batch.vis_poses), batch.n_vis, batch.scans.shape[-1])
-        self._ck(self.L.velo_gpu_batch_frontend(self.h, slot0, batch.count, C.addressof(bi), chunk, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
+        if kpwd is None:
+            self._ck(self.L.velo_gpu_batch_frontend(self.h, slot0, batch.count, C.addressof(bi), chunk, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth), _ptr(n_hits)))
+        else:
+            self._ck(self.L.velo_gpu_batch_frontend_kpwd(self.h, slot0, batch.count, C.addressof(bi), chunk, _ptr(icp_neq), _ptr(vis_neq), _ptr(has_depth),
+                                                         _ptr(n_hits), _ptr(kpwd)))
 
     def batch_frame_to_frame(self, slot0, count, transforms, enable_visual=1, enable_icp=1, first_has_prev=0):
         """velo.h:616-907 for every frame pair of the batch at once; transforms [count][6] -> (transforms, [report dict per slot])"""

@@ -17,6 +17,7 @@ struct ProfRec { int k; cudaEvent_t a, b; };
 struct velo_gpu_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;   // stream2: every other chunk of batch_frontend
+    cudaStream_t d2h_stream = nullptr;                                         // keypoints_with_depth of finished chunks travel back while later chunks compute
     cudaStream_t launch_stream = nullptr;                                        // stream of the launch being profiled
     std::vector<cudaEvent_t> chunk_ev;
     cudaEvent_t fe_up0 = nullptr, fe_up1 = nullptr, fe_c0 = nullptr, fe_c1 = nullptr;   // batch_frontend: upload / whole-call timing of the last call
@@ -370,6 +371,7 @@ extern "C" int velo_gpu_destroy(velo_gpu_ctx *ctx) {
     for (cudaEvent_t e : { ctx->fe_up0, ctx->fe_up1, ctx->fe_c0, ctx->fe_c1 }) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VELO_OK;
@@ -1178,12 +1180,37 @@ extern "C" int velo_gpu_batch_download(velo_gpu_ctx *ctx, int slot0, int count, 
     return VELO_OK;
 }
 
+// keypoints_with_depth of the batch (velo.h:479 hands this cloud to the caller): [count][sets][cams][max_features] float4 {x, y, z, 1};
+// the first n_hits[slot][set][cam] records of an image are valid, in keypoint order (has_depth[k] = index into them, velo.h:480)
+extern "C" int velo_gpu_batch_download_kpwd(velo_gpu_ctx *ctx, int slot0, int count, float *kpwd) {
+    if (!ctx || !kpwd) return VELO_ERR_INVALID_ARG;
+    if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const DevBuffers &B = ctx->B;
+    const size_t per = VELO_NUM_KP_SETS * (size_t)B.C * B.F;
+    CK(cudaMemcpyAsync(kpwd, B.kpwd + (size_t)slot0 * per, (size_t)count * per * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VELO_OK;
+}
+
 // upload -> run -> download of a whole batch with the uploads of chunk c+1 overlapping the kernels of chunk c
 // tuning aid (tools/): VELO_FE_UPLOAD_REPEAT=k copies every chunk k times, which puts one GPU into the copy-bound regime that eight
 // GPUs sharing a host are in
 static int fe_upload_repeat() { static const int r = [] { const char *e = getenv("VELO_FE_UPLOAD_REPEAT"); return e ? std::max(1, atoi(e)) : 1; }(); return r; }
+static int batch_frontend_impl(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
+                               double *icp_neq, double *vis_neq, int *has_depth, int *n_hits, float *kpwd);
 extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
                                        double *icp_neq, double *vis_neq, int *has_depth, int *n_hits) {
+    return batch_frontend_impl(ctx, slot0, count, in, chunk, icp_neq, vis_neq, has_depth, n_hits, nullptr);
+}
+// the same call that also returns keypoints_with_depth (layout of velo_gpu_batch_download_kpwd); each chunk's cloud is copied back on
+// its own stream as soon as the chunk's association stage is done, under the kernels of the later chunks
+extern "C" int velo_gpu_batch_frontend_kpwd(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
+                                            double *icp_neq, double *vis_neq, int *has_depth, int *n_hits, float *kpwd) {
+    return batch_frontend_impl(ctx, slot0, count, in, chunk, icp_neq, vis_neq, has_depth, n_hits, kpwd);
+}
+static int batch_frontend_impl(velo_gpu_ctx *ctx, int slot0, int count, const velo_batch_inputs *in, int chunk,
+                               double *icp_neq, double *vis_neq, int *has_depth, int *n_hits, float *kpwd) {
     if (!ctx || !in) return VELO_ERR_INVALID_ARG;
     if (check_range(ctx, slot0, count)) return VELO_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1238,6 +1265,13 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
         rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], light, 1);
         if (rc) return rc;
         CK(cudaEventRecord(ev_light[c], st));
+        if (kpwd) {
+            if (!ctx->d2h_stream) CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+            const size_t per = VELO_NUM_KP_SETS * (size_t)ctx->B.C * ctx->B.F;
+            CK(cudaStreamWaitEvent(ctx->d2h_stream, ev_light[c], 0));
+            CK(cudaMemcpyAsync(kpwd + (size_t)cut[c] * per * 4, ctx->B.kpwd + (size_t)(slot0 + cut[c]) * per, (size_t)(cut[c + 1] - cut[c]) * per * sizeof(float4),
+                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
         if (trace) cudaEventRecord(tr[3 * c + 1], st);
         if (c > 0) CK(cudaStreamWaitEvent(st, ev_light[c - 1], 0));
         rc = run_stages(ctx, L, slot0 + cut[c], cut[c + 1] - cut[c], VELO_STAGE_ICP | VELO_STAGE_VISUAL, 1);
@@ -1248,6 +1282,7 @@ extern "C" int velo_gpu_batch_frontend(velo_gpu_ctx *ctx, int slot0, int count, 
     if (two) { CK(cudaEventRecord(ev_light[nchunks], ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ev_light[nchunks], 0)); }
     ctx->launch_stream = ctx->stream;
     const int rc = velo_gpu_batch_download(ctx, slot0, count, icp_neq, vis_neq, has_depth, n_hits);
+    if (kpwd) CK(cudaStreamSynchronize(ctx->d2h_stream));
     if (trace) {
         cudaDeviceSynchronize();
         fprintf(stderr, "[fe] growth %.2f, %d chunks: size copy_done light_done icp_done (ms)\n", ctx->fe_growth, nchunks);

@@ -148,19 +148,30 @@ __host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(
 // time (the array otherwise lives in local memory because it is indexed by a runtime word number; measured 4 % of the kernel).
 // STATS = true: candidates / rings / mask bits per pass are counted into slots 60..62 of the records (1.6 % of the kernel; off by default,
 // velo_gpu_search_stats_enable)
+struct IcpShared {
+    int q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
+    int rsM[VELO_MAX_RINGS_HARD + 1];
+    int rsS[VELO_MAX_RINGS_HARD + 1];    // ring starts of the target scan (seeds and the third point read them every pass)
+    double rows[ICP_THREADS / 32][NEQ_STAGE];
+    double acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
+    unsigned stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];             // per warp and run: no atomics
+    IcpPass pass[VELO_MAX_PASSES];
+    int next;
+    double loss[4];                       // loss constants of the unit: a^2, 1/a^2, w a^2/2, w
+};
 template <bool RECORDS, bool W1, bool STATS>
-__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
-                                                          double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
-                                                          IcpFrozen *__restrict__ frozen, int frozen_stride) {
-    __shared__ int s_q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
-    __shared__ int s_rsM[VELO_MAX_RINGS_HARD + 1];
-    __shared__ int s_rsS[VELO_MAX_RINGS_HARD + 1];    // ring starts of the target scan (seeds and the third point read them every pass)
-    __shared__ double s_rows[ICP_THREADS / 32][NEQ_STAGE];
-    __shared__ double s_acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
-    __shared__ unsigned s_stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];             // per warp and run: no atomics
-    __shared__ IcpPass s_pass[VELO_MAX_PASSES];
-    __shared__ int s_next;
-    __shared__ double s_loss[4];                       // loss constants of the unit: a^2, 1/a^2, w a^2/2, w
+__device__ __forceinline__ void icp_pass_body(IcpShared &sh, const DevBuffers &B, const DevCalib &cal, const IcpUnit *__restrict__ units,
+                                              double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
+                                              IcpFrozen *__restrict__ frozen, int frozen_stride) {
+    int (&s_q)[VELO_MAX_RINGS_HARD + 1] = sh.q;
+    int (&s_rsM)[VELO_MAX_RINGS_HARD + 1] = sh.rsM;
+    int (&s_rsS)[VELO_MAX_RINGS_HARD + 1] = sh.rsS;
+    double (&s_rows)[ICP_THREADS / 32][NEQ_STAGE] = sh.rows;
+    double (&s_acc)[ICP_THREADS / 32][VELO_MAX_PASSES][56] = sh.acc;
+    unsigned (&s_stat)[ICP_THREADS / 32][VELO_MAX_PASSES][5] = sh.stat;
+    IcpPass (&s_pass)[VELO_MAX_PASSES] = sh.pass;
+    int &s_next = sh.next;
+    double (&s_loss)[4] = sh.loss;
     const IcpUnit &U = units[blockIdx.y];
     if (threadIdx.x == 0) { s_next = 0; const double bb = U.loss_a * U.loss_a; s_loss[0] = bb; s_loss[1] = 1.0 / bb; s_loss[2] = 0.5 * U.weight * bb; s_loss[3] = U.weight; }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -191,11 +202,11 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     const float4 *ptsS = B.pts + (size_t)U.tgt_slot * B.N;
     const float4 *sorted = B.sorted + (size_t)U.tgt_slot * B.N;
     const int *csS = B.cell_start + (size_t)U.tgt_slot * B.R * (VELO_AZ_BINS + 1);
-    const int W = W1 ? 1 : B.W;
-    const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
-    const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * W;
-    const u64 *rloS = B.rmask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
-    const u64 *rhiS = B.rmask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * W;
+    const int W = W1 ? 1 : B.W, WS = B.W;      // words visited / words per table entry (a context for 128 rings holds 64-ring scans too)
+    const u64 *mloS = B.mask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * WS;
+    const u64 *mhiS = B.mask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_EL_BUCKETS * WS;
+    const u64 *rloS = B.rmask_lo + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * WS;
+    const u64 *rhiS = B.rmask_hi + (size_t)U.tgt_slot * VELO_SECTORS * VELO_RG_BUCKETS * WS;
 
     for (;;) {
         int run = 0;
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                     const int eb0 = el_bucket(el - ICP_CELLSEED_TOL), eb1 = el_bucket(el + ICP_CELLSEED_TOL);
                     int s1 = -1, s2 = -1;
                     for (int wd = 0; wd < W && s2 < 0; wd++) {
-                        u64 m = __ldg(mloS + (size_t)(base + eb1) * W + wd) & __ldg(mhiS + (size_t)(base + eb0) * W + wd);
+                        u64 m = __ldg(mloS + (size_t)(base + eb1) * WS + wd) & __ldg(mhiS + (size_t)(base + eb0) * WS + wd);
                         if (m != 0ull && s1 < 0) { s1 = wd * 64 + __ffsll((long long)m) - 1; m &= m - 1; }
                         if (m != 0ull && s1 >= 0) s2 = wd * 64 + __ffsll((long long)m) - 1;
                     }
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
                                 lev = started ? lev * ICP_LEVMUL : (tight ? 8.0f : ICP_LEV0);
                                 started = true; word = 0; gcur = fminf(lev, w.gam);
                             }
-                            m = ring_mask(mloS, mhiS, rloS, rhiS, W, word, w, mask_query(el, gcur, rho, sqrt_ap(bound)), true) & ~V[word];
+                            m = ring_mask(mloS, mhiS, rloS, rhiS, WS, word, w, mask_query(el, gcur, rho, sqrt_ap(bound)), true) & ~V[word];
                             V[word] |= m;
                             continue;
                         }
@@ -494,6 +505,20 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuf
     }
 }
 
+// The kernel proper: a frame pair whose target scan has at most 64 rings takes the single-word body even in a context created for more
+// (the drop-in default is 128 rings, because kitti.h:166-173 can split a sweep into a few more than 64); uniform per CTA.
+// (ONE = true: a context for at most 64 rings — only the single-word body is compiled in, which keeps its register allocation to itself:
+// 0.6 % at the bench configuration.)
+template <bool RECORDS, bool STATS, bool ONE>
+__global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
+                                                          double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
+                                                          IcpFrozen *__restrict__ frozen, int frozen_stride) {
+    __shared__ IcpShared sh;
+    const int tgt = units[blockIdx.y].tgt_slot;
+    if (ONE || (tgt >= 0 && B.n_rings[tgt] <= 64)) icp_pass_body<RECORDS, true, STATS>(sh, B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    else if (!ONE) icp_pass_body<RECORDS, false, STATS>(sh, B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+}
+
 // fixed-order sum of the per-run records of one (unit, pass): out[unit][pass][0..62]
 __global__ void __launch_bounds__(256) k_neq_reduce(DevBuffers B, const IcpUnit *__restrict__ units, const double *__restrict__ partial, int runs_cap,
                                                     double *__restrict__ out, int out_stride_passes) {
@@ -532,10 +557,11 @@ void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, con
     const int runs_cap = icp_runs_cap(B.N);
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
-    const bool rec = corr || frozen, w1 = B.W == 1;
-#define ICP_LAUNCH(R_, W_, S_) k_icp_pass<R_, W_, S_><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0)
-    if (stats) { if (rec && w1) ICP_LAUNCH(true, true, true); else if (rec) ICP_LAUNCH(true, false, true); else if (w1) ICP_LAUNCH(false, true, true); else ICP_LAUNCH(false, false, true); }
-    else { if (rec && w1) ICP_LAUNCH(true, true, false); else if (rec) ICP_LAUNCH(true, false, false); else if (w1) ICP_LAUNCH(false, true, false); else ICP_LAUNCH(false, false, false); }
+    const bool rec = corr || frozen;
+#define ICP_LAUNCH(R_, S_) do { if (B.W == 1) k_icp_pass<R_, S_, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0); \
+                                 else k_icp_pass<R_, S_, false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0); } while (0)
+    if (stats) { if (rec) ICP_LAUNCH(true, true); else ICP_LAUNCH(false, true); }
+    else { if (rec) ICP_LAUNCH(true, false); else ICP_LAUNCH(false, false); }
 #undef ICP_LAUNCH
     if (L.post) L.post(L.user, VK_ICP_PASS);
     dim3 g2(n_units, n_pass);

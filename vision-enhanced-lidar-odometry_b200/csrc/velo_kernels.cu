@@ -474,19 +474,26 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
             unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
             const int cnt = s_cnt[s];
             float xprev = 0.f; int bprev = -1;                               // last point of the previous 32 (lane 31's)
-            for (int i0 = 0; i0 <= cnt; i0 += 32) {
+            int bfirst = ASSOC_NB, blast = ASSOC_NB;                         // (an empty ring: every entry is 0 = cnt)
+            for (int i0 = 0; i0 < cnt; i0 += 32) {
                 const int i = i0 + lane;
                 const bool in = i < cnt;
                 const float xi = in ? ps[i].x : 0.f;
                 const int bi = in ? assoc_xbucket(xi, xmin, xscale) : ASSOC_NB;
                 float xp = __shfl_up_sync(FULL, xi, 1); int bp = __shfl_up_sync(FULL, bi, 1);
                 if (lane == 0) { xp = xprev; bp = bprev; }
-                if (i <= cnt) {
-                    if (i > 0 && in && xp > xi) s_mono[s] = 0;
+                if (in && i > 0) {                                           // the gap between two neighbours: usually empty or one bucket
+                    if (xp > xi) s_mono[s] = 0;
                     for (int b = bp + 1; b <= bi; b++) lut[b] = (unsigned short)i;
                 }
+                if (i0 == 0) bfirst = __shfl_sync(FULL, bi, 0);
+                blast = __shfl_sync(FULL, bi, min(31, cnt - 1 - i0));
                 xprev = __shfl_sync(FULL, xi, 31); bprev = __shfl_sync(FULL, bi, 31);
             }
+            // the buckets up to the first point's and beyond the last point's (most of the table for a ring that crosses only part of
+            // the image) are filled by all lanes instead of by the first / last point's lane alone
+            for (int b = lane; b <= bfirst; b += 32) lut[b] = 0;
+            for (int b = blast + 1 + lane; b <= ASSOC_NB; b += 32) lut[b] = (unsigned short)cnt;
         }
         __syncthreads();
         // zone ranges: one thread per (ring, zone).  On a ring with non-decreasing x the points whose x lies in the zone widened by
@@ -515,17 +522,24 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
         s_pair[p] = pr;
     }
     __syncthreads();
-    for (int bkt = tid; bkt <= ASSOC_YB; bkt += blockDim.x) {
+    for (int bkt = wid; bkt <= ASSOC_YB; bkt += nwarps) {               // a warp per bucket, a lane per ring: the mask is a ballot
         const float y0 = ymin + bkt / yscale - 1e-4f, y1 = ymin + (bkt + 1) / yscale + 1e-4f;   // bucket edges, padded
 #pragma unroll
         for (int w = 0; w < ASSOC_MAXW; w++) {
             unsigned long long m = 0ull;
-            for (int s2 = 64 * w; s2 < min(nr, 64 * w + 64); s2++) {
-                const float2 pa = s_pair[s2], pb = s_pair[s2 + 1];
-                const bool need = bkt == ASSOC_YB || (pa.x <= y1 && y0 < pa.y) || (pb.x <= y1 && y0 < pb.y);
-                if (need && s_cnt[s2] > 1) m |= 1ull << (s2 & 63);                               // rings with <= 1 points: velo.h:400-403
+            if (64 * w < nr) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int s2 = 64 * w + 32 * h + lane;
+                    bool need = false;
+                    if (s2 < nr && s_cnt[s2] > 1) {                                              // rings with <= 1 points: velo.h:400-403
+                        const float2 pa = s_pair[s2], pb = s_pair[s2 + 1];
+                        need = bkt == ASSOC_YB || (pa.x <= y1 && y0 < pa.y) || (pb.x <= y1 && y0 < pb.y);
+                    }
+                    m |= (unsigned long long)__ballot_sync(FULL, need) << (32 * h);
+                }
             }
-            s_need[bkt][w] = m;
+            if (lane == 0) s_need[bkt][w] = m;
         }
     }
     // 2-D table: one thread per (pair, zone) marks both rings of the pair in the y buckets the pair can be hit from in that zone
@@ -573,7 +587,14 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_assoc_search(DevBuffers B, De
                         const unsigned short *lut = s_lut + s * (ASSOC_NB + 1);
                         int j = lut[xb];
                         const int j1 = lut[xb + 1];
-                        while (j < j1 && ps[j].x <= kp.x) j++;                      // the keypoint's own bucket, ~2 points
+                        // the keypoint's own bucket (~2 points): x does not decrease along the ring, so "x <= kp.x" holds for a prefix of the
+                        // bucket and counting it four points at a time is one instruction stream for the whole warp
+                        for (;;) {
+                            const int j0 = j;
+#pragma unroll
+                            for (int t = 0; t < 4; t++) j += (int)((j0 + t < j1) & (ps[max(min(j0 + t, j1 - 1), 0)].x <= kp.x));
+                            if (j != j0 + 4) break;
+                        }
                         mid = j - 1;
                         found = mid >= 0 && mid <= cnt - 2;
                         if (found) { a = ps[mid]; b = ps[mid + 1]; }

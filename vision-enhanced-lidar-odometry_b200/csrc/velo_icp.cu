@@ -148,25 +148,29 @@ __host__ __device__ inline int icp_runs_cap(int max_points) { return icp_blocks(
 // time (the array otherwise lives in local memory because it is indexed by a runtime word number; measured 4 % of the kernel).
 // STATS = true: candidates / rings / mask bits per pass are counted into slots 60..62 of the records (1.6 % of the kernel; off by default,
 // velo_gpu_search_stats_enable)
+// Shared memory of a CTA.  RINGS = ring capacity + 1 of the instantiation (65 for a context of at most 64 rings): with the
+// staging area below that keeps three resident CTAs under 132 KB, i.e. one shared-memory carve-out step lower = 32 KB more L1.
+#define ICP_STAGE (8 * 36)               /* per warp: 6 Jacobian columns + residual + weight, 32 rows padded to 36 */
+template <int RINGS>
 struct IcpShared {
-    int q[VELO_MAX_RINGS_HARD + 1];      // query prefix per source ring
-    int rsM[VELO_MAX_RINGS_HARD + 1];
-    int rsS[VELO_MAX_RINGS_HARD + 1];    // ring starts of the target scan (seeds and the third point read them every pass)
-    double rows[ICP_THREADS / 32][NEQ_STAGE];
+    int q[RINGS];                        // query prefix per source ring
+    int rsM[RINGS];
+    int rsS[RINGS];                      // ring starts of the target scan (seeds and the third point read them every pass)
+    double rows[ICP_THREADS / 32][ICP_STAGE];
     double acc[ICP_THREADS / 32][VELO_MAX_PASSES][56];               // sums of the warp's current run
     unsigned stat[ICP_THREADS / 32][VELO_MAX_PASSES][5];             // per warp and run: no atomics
     IcpPass pass[VELO_MAX_PASSES];
     int next;
     double loss[4];                       // loss constants of the unit: a^2, 1/a^2, w a^2/2, w
 };
-template <bool RECORDS, bool W1, bool STATS>
-__device__ __forceinline__ void icp_pass_body(IcpShared &sh, const DevBuffers &B, const DevCalib &cal, const IcpUnit *__restrict__ units,
+template <bool RECORDS, bool W1, bool STATS, int RINGS>
+__device__ __forceinline__ void icp_pass_body(IcpShared<RINGS> &sh, const DevBuffers &B, const DevCalib &cal, const IcpUnit *__restrict__ units,
                                               double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
                                               IcpFrozen *__restrict__ frozen, int frozen_stride) {
-    int (&s_q)[VELO_MAX_RINGS_HARD + 1] = sh.q;
-    int (&s_rsM)[VELO_MAX_RINGS_HARD + 1] = sh.rsM;
-    int (&s_rsS)[VELO_MAX_RINGS_HARD + 1] = sh.rsS;
-    double (&s_rows)[ICP_THREADS / 32][NEQ_STAGE] = sh.rows;
+    int (&s_q)[RINGS] = sh.q;
+    int (&s_rsM)[RINGS] = sh.rsM;
+    int (&s_rsS)[RINGS] = sh.rsS;
+    double (&s_rows)[ICP_THREADS / 32][ICP_STAGE] = sh.rows;
     double (&s_acc)[ICP_THREADS / 32][VELO_MAX_PASSES][56] = sh.acc;
     unsigned (&s_stat)[ICP_THREADS / 32][VELO_MAX_PASSES][5] = sh.stat;
     IcpPass (&s_pass)[VELO_MAX_PASSES] = sh.pass;
@@ -451,13 +455,13 @@ __device__ __forceinline__ void icp_pass_body(IcpShared &sh, const DevBuffers &B
                 __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 6; c++) S[c * 36 + lane] = kept ? J[c] : 0.0;
-                S[6 * 36 + lane] = kept ? res : 0.0; S[7 * 36 + lane] = 0.0; S[8 * 36 + lane] = kept ? rho1 : 0.0;
+                S[6 * 36 + lane] = kept ? res : 0.0; S[7 * 36 + lane] = kept ? rho1 : 0.0;     // (column 7 of X is zero and is not staged)
                 __syncwarp();
                 const int fr = lane >> 2, fk = lane & 3;
                 double cr0 = 0.0, cr1 = 0.0, cw0 = 0.0, cw1 = 0.0;
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    const double x = S[fr * 36 + 4 * t + fk], wgt = S[8 * 36 + 4 * t + fk];
+                    const double wgt = S[7 * 36 + 4 * t + fk], x = fr < 7 ? S[fr * 36 + 4 * t + fk] : 0.0;
                     const double xw = x * wgt;
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cr0), "+d"(cr1) : "d"(x), "d"(x));
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cw0), "+d"(cw1) : "d"(x), "d"(xw));
@@ -513,10 +517,11 @@ template <bool RECORDS, bool STATS, bool ONE>
 __global__ void __launch_bounds__(ICP_THREADS, ICP_MIN_BLOCKS) k_icp_pass(DevBuffers B, DevCalib cal, const IcpUnit *__restrict__ units,
                                                           double *__restrict__ partial, int runs_cap, velo_icp_corr *__restrict__ corr, int corr_stride,
                                                           IcpFrozen *__restrict__ frozen, int frozen_stride) {
-    __shared__ IcpShared sh;
+    constexpr int RINGS = (ONE ? 64 : VELO_MAX_RINGS_HARD) + 1;
+    __shared__ IcpShared<RINGS> sh;
     const int tgt = units[blockIdx.y].tgt_slot;
-    if (ONE || (tgt >= 0 && B.n_rings[tgt] <= 64)) icp_pass_body<RECORDS, true, STATS>(sh, B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
-    else if (!ONE) icp_pass_body<RECORDS, false, STATS>(sh, B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    if (ONE || (tgt >= 0 && B.n_rings[tgt] <= 64)) icp_pass_body<RECORDS, true, STATS, RINGS>(sh, B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
+    else if (!ONE) icp_pass_body<RECORDS, false, STATS, RINGS>(sh, B, cal, units, partial, runs_cap, corr, corr_stride, frozen, frozen_stride);
 }
 
 // fixed-order sum of the per-run records of one (unit, pass): out[unit][pass][0..62]
@@ -558,7 +563,10 @@ void launch_icp(const Launcher &L, const DevBuffers &B, const DevCalib &cal, con
     dim3 g(ctas, n_units);
     if (L.pre) L.pre(L.user, VK_ICP_PASS);
     const bool rec = corr || frozen;
-#define ICP_LAUNCH(R_, S_) do { if (B.W == 1) k_icp_pass<R_, S_, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0); \
+    // (The single-word kernel's three resident CTAs fit the 132 KB shared-memory carve-out, which the driver selects on its own; measured
+    // with the carve-out forced: 132 KB 82.5 ms, 164 KB 86.1 / 88.3 ms, 228 KB 91.8 ms per 1000 pairs x 6 passes — L1 capacity matters.)
+#define ICP_LAUNCH(R_, S_) do { \
+                                 if (B.W == 1) k_icp_pass<R_, S_, true><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0); \
                                  else k_icp_pass<R_, S_, false><<<g, ICP_THREADS, 0, L.stream>>>(B, cal, units, partial, runs_cap, rec ? corr : nullptr, rec ? corr_stride : 0, rec ? frozen : nullptr, rec ? frozen_stride : 0); } while (0)
     if (stats) { if (rec) ICP_LAUNCH(true, true); else ICP_LAUNCH(false, true); }
     else { if (rec) ICP_LAUNCH(true, false); else ICP_LAUNCH(false, false); }

@@ -6,6 +6,8 @@ agree on random and adversarial inputs:
                    pop / skip / push of velo.h:351-368
 * k_assoc_search : the binary search of velo.h:404-412 without early `continue`s (both neighbours read, lo / hi by selects)
 * k_icp_pass     : the running best as one unsigned 64-bit (bits of d2, index) minimum == smallest d2, ties to the lower index;
+                   the branch-free insertion of per-ring results into the two smallest keys == the reference's streaming top-2 over
+                   ascending rings (velo.h:825-848), in ANY visiting order, and a bound taken from two seed points never cuts it off;
                    the range bucket taken from the float's bits is monotone; the partition of the queries into blocks / runs
                    covers every query exactly once for any number of CTAs
 """
@@ -125,6 +127,68 @@ def test_u64_key_minimum_is_smallest_distance_then_lowest_index(seed, n, ties):
         m = d2[ok].min()
         assert np.uint32(int(best) >> 32).view(f32) == m
         assert (int(best) & 0xFFFFFFFF) == idx[ok & (d2 == m)].min()
+
+
+# ------------------------------------------------------------------------------------------------ top-2 rings
+def top2_reference(per_ring):
+    """velo.h:825-848: rings in ascending order, strict `<` against the running best two distances"""
+    inf = float("inf")
+    di, dj, si, sj, ni, nj = inf, inf, -1, -1, -1, -1
+    for s, (d, n) in enumerate(per_ring):
+        if d is None: continue
+        if d < di: dj, sj, nj = di, si, ni; di, si, ni = d, s, n
+        elif d < dj: dj, sj, nj = d, s, n
+    return (si, ni), (sj, nj)
+
+
+@settings(**SET)
+@given(seed=st.integers(0, 10**6), n_rings=st.integers(1, 70), ties=st.booleans(), seeded=st.booleans())
+def test_branch_free_top2_insertion_equals_streaming_top2(seed, n_rings, ties, seeded):
+    """Every ring is visited once and hands in its nearest point inside the threshold as the key (bits of d2 | ring | index); the
+    kernel keeps the two smallest keys with lo = min(k, ki), hi = max(k, ki), ki = lo, kj = min(kj, hi), in whatever order the
+    rings come (nearest elevation first, several mask levels).  With a seed bound (the farther of two real points of different
+    rings) rings whose nearest point lies beyond the bound are never visited: the result must not change."""
+    rng = np.random.default_rng(seed)
+    IDX_BITS = 20
+    d = rng.uniform(0, 0.5, n_rings).astype(f32)
+    if ties: d = (np.round(d * 8) / 8).astype(f32)
+    has = rng.random(n_rings) < 0.7                                # rings with a point inside the threshold
+    idx = rng.integers(0, 2000, n_rings)
+    per_ring = [(float(d[s]), int(idx[s])) if has[s] else (None, None) for s in range(n_rings)]
+    (si, ni), (sj, nj) = top2_reference(per_ring)
+    INF = (1 << 64) - 1
+    key = lambda s: (int(d[s].view(np.uint32)) << 32) | (s << IDX_BITS) | int(idx[s])
+    bound = None
+    if seeded and has.sum() >= 2:                                  # any two rings with points: the farther one bounds the runner-up
+        a, b = rng.choice(np.nonzero(has)[0], 2, replace=False)
+        bound = max(d[a], d[b])
+    ki = kj = INF
+    for s in rng.permutation(n_rings):
+        if not has[s] or (bound is not None and d[s] > bound): continue
+        k = key(s); lo, hi = min(k, ki), max(k, ki)
+        ki, kj = lo, min(kj, hi)
+    ring = lambda k: -1 if k == INF else (k & 0xFFFFFFFF) >> IDX_BITS
+    pidx = lambda k: -1 if k == INF else k & ((1 << IDX_BITS) - 1)
+    assert (ring(ki), pidx(ki)) == (si, ni)
+    assert (ring(kj), pidx(kj)) == (sj, nj)
+
+
+# ------------------------------------------------------------------------------------------------ window half-width
+def test_asin_upper_bound_survives_the_approximate_arithmetic():
+    """asin_ub(x) = x / sqrt(1 - x^2) * (1 + 4e-6) + 3e-5 sizes the azimuth window / elevation tolerance of a query (csrc/velo_icp.cu).
+    Its input b / D comes from the 2-ulp hardware square root and division and its rsqrt is the 2-ulp MUFU one: with every one of
+    those errors at its worst (1e-6 relative on x, 5e-7 on the rsqrt, float rounding of each step) the result must still exceed
+    asin(x) by the 1e-5 rad kept for the polynomial atan2_q, for every x the kernel does not already treat as 'full circle'."""
+    x = np.concatenate([np.linspace(0.0, 0.999, 200001), np.geomspace(1e-9, 1e-2, 2001)])
+    worst = np.inf
+    for ex in (-1e-6, 1e-6):
+        for er in (-5e-7, 5e-7):
+            xa = (x * (1 + ex)).astype(f32)                                            # what the kernel computed for the true x
+            t = (f32(1.0) - (xa * xa).astype(f32)).astype(f32)
+            rs = ((1.0 / np.sqrt(t.astype(np.float64))) * (1 + er)).astype(f32)
+            ub = (((xa * rs).astype(f32) * f32(1.0 + 4e-6)).astype(f32) + f32(3e-5)).astype(f32)
+            worst = min(worst, float((ub.astype(np.float64) - np.arcsin(x) - 1e-5).min()))
+    assert worst > 0.0, worst
 
 
 # ------------------------------------------------------------------------------------------------ range buckets

@@ -4,7 +4,9 @@ agree on random and adversarial inputs:
 
 * k_project      : runs of survivors with non-decreasing canonical x are pushed in bulk, out-of-order points replay the scalar
                    pop / skip / push of velo.h:351-368
-* k_assoc_search : the binary search of velo.h:404-412 without early `continue`s (both neighbours read, lo / hi by selects)
+* k_assoc_search : the binary search of velo.h:404-412 without early `continue`s (both neighbours read, lo / hi by selects); the
+                   x table of a ring (gaps by the lanes, head / tail by the whole warp) + the prefix count over the keypoint's
+                   own bucket == that search on a ring whose x never decreases
 * k_icp_pass     : the running best as one unsigned 64-bit (bits of d2, index) minimum == smallest d2, ties to the lower index;
                    the branch-free insertion of per-ring results into the two smallest keys == the reference's streaming top-2 over
                    ascending rings (velo.h:825-848), in ANY visiting order, and a bound taken from two seed points never cuts it off;
@@ -105,6 +107,63 @@ def test_uniform_binary_search_equals_reference(seed, n, sorted_, quant):
     px = px.astype(f32)
     for kx in list(rng.uniform(-1.1, 1.1, 20).astype(f32)) + [px[0], px[-1], px[n // 2]]:
         assert search_uniform(px, kx) == search_reference(px, kx)
+
+
+# ------------------------------------------------------------------------------------------------ x table of a ring
+NB = 128
+
+
+def xbucket(x, xmin, xscale):
+    return int(min(max(int((f32(x) - f32(xmin)) * f32(xscale)), 0), NB - 1))
+
+
+def lut_build(px, xmin, xscale):
+    """k_assoc_search: lane i > 0 fills the buckets between its predecessor's and its own, the warp fills the head and the tail"""
+    cnt = len(px)
+    lut = [None] * (NB + 1)
+    b = [xbucket(x, xmin, xscale) for x in px]
+    for i in range(1, cnt):
+        for k in range(b[i - 1] + 1, b[i] + 1): lut[k] = i
+    bfirst, blast = (b[0], b[-1]) if cnt else (NB, NB)
+    for k in range(0, bfirst + 1): lut[k] = 0
+    for k in range(blast + 1, NB + 1): lut[k] = cnt
+    return lut
+
+
+def lut_search(px, lut, kx, xmin, xscale):
+    """two table reads + the prefix count over the bucket, four points at a time"""
+    xb = xbucket(kx, xmin, xscale)
+    j, j1 = lut[xb], lut[xb + 1]
+    while True:
+        j0 = j
+        for t in range(4):
+            jj = max(min(j0 + t, j1 - 1), 0)
+            j += int(j0 + t < j1 and px[jj] <= kx)
+        if j != j0 + 4: break
+    mid = j - 1
+    return mid if 0 <= mid <= len(px) - 2 else None
+
+
+@settings(**SET)
+@given(seed=st.integers(0, 10**6), n=st.integers(2, 300), span=st.sampled_from([0.05, 0.4, 1.0]), dup=st.booleans())
+def test_x_table_search_equals_reference_on_a_monotone_ring(seed, n, span, dup):
+    rng = np.random.default_rng(seed)
+    xmin, xmax = f32(-0.9), f32(0.9)
+    xscale = f32(NB) / (xmax - xmin)
+    lo = rng.uniform(-1.0, 1.0 - span)                                 # rings that cross only part of the image, or leave it
+    px = np.sort(rng.uniform(lo, lo + span, n)).astype(f32)
+    if dup: px = (np.round(px * 64) / 64).astype(f32)                  # duplicated x (velo.h:360-366 pushes z ties)
+    lut = lut_build(px, xmin, xscale)
+    for k in range(NB + 1):                                            # the definition: first index whose bucket is >= k
+        first = next((i for i in range(n) if xbucket(px[i], xmin, xscale) >= k), n)
+        assert lut[k] == first
+    for kx in np.concatenate([rng.uniform(-1.1, 1.1, 30), px[rng.integers(0, n, 10)]]).astype(f32):
+        want = search_reference(px, kx)
+        got = lut_search(px, lut, kx, xmin, xscale)
+        if want >= 0:                                                  # px[mid] <= kx < px[mid+1] has one solution on a monotone ring
+            assert got == want and px[got] <= kx < px[got + 1]
+        else:
+            assert got is None
 
 
 # ------------------------------------------------------------------------------------------------ 64-bit running best
